@@ -1,0 +1,233 @@
+"""ctypes binding of the C-ABI shared library (include/linemod_b200.h).
+
+Fails loudly when the library is missing or cannot be loaded: there is no CPU / PyTorch fallback
+for the hot path.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liblinemod_b200.so")
+
+LM_OK, LM_E_INVALID, LM_E_CUDA, LM_E_STATE, LM_E_CAPACITY = 0, -1, -2, -3, -4
+
+MATCH_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("similarity", "<f4"), ("class_index", "<i4"), ("template_id", "<i4")])
+RECORD_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("similarity", "<f4"), ("work", "<i4")])
+
+# every symbol include/linemod_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "lm_last_error", "lm_create", "lm_destroy", "lm_load_bank", "lm_select", "lm_shard_range",
+    "lm_upload_quantized", "lm_run", "lm_enqueue", "lm_complete", "lm_device_records", "lm_fetch_records",
+    "lm_finish", "lm_match_quantized", "lm_debug_linear_memories", "lm_counters", "lm_set_timing",
+    "lm_stage_times", "lm_stream", "lm_launch_count",
+]
+
+_lib = None
+
+
+class LinemodLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load liblinemod_b200.so (built in-tree by `make -C 6dpose_b200/csrc` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LinemodLibraryError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback for the LINEMOD hot path." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    c_int, c_i64, c_f, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    u8pp = ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8))
+    L.lm_last_error.restype = ctypes.c_char_p
+    L.lm_create.argtypes = [c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(vp)]
+    L.lm_destroy.argtypes = [vp]
+    L.lm_destroy.restype = None
+    L.lm_load_bank.argtypes = [vp, c_int, i32p, c_int, i32p, i32p, c_i64]
+    L.lm_select.argtypes = [vp, i32p, c_int, c_int, c_int]
+    L.lm_shard_range.argtypes = [vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
+    L.lm_upload_quantized.argtypes = [vp, u8pp, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
+    L.lm_run.argtypes = [vp, c_f]
+    L.lm_enqueue.argtypes = [vp, c_f]
+    L.lm_complete.argtypes = [vp]
+    L.lm_device_records.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(c_i64)]
+    L.lm_fetch_records.argtypes = [vp, vp, c_i64, ctypes.POINTER(c_i64)]
+    L.lm_finish.argtypes = [vp, vp, c_i64, vp, c_i64, ctypes.POINTER(c_i64)]
+    L.lm_match_quantized.argtypes = [vp, u8pp, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_f, vp, c_i64,
+                                     ctypes.POINTER(c_i64)]
+    L.lm_debug_linear_memories.argtypes = [vp, c_int, c_int, ctypes.POINTER(ctypes.c_uint8), c_i64]
+    L.lm_counters.argtypes = [vp, ctypes.POINTER(c_i64)]
+    L.lm_set_timing.argtypes = [vp, c_int]
+    L.lm_stage_times.argtypes = [vp, ctypes.POINTER(c_f)]
+    L.lm_stream.argtypes = [vp]
+    L.lm_stream.restype = vp
+    L.lm_launch_count.argtypes = [vp]
+    L.lm_launch_count.restype = c_i64
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is ctypes.c_int and name not in ("lm_last_error",):
+            fn.restype = c_int
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc == LM_OK:
+        return
+    msg = load().lm_last_error().decode("utf-8", "replace")
+    if rc == LM_E_INVALID:
+        raise RuntimeError(msg)  # the reference raises cv::Exception -> RuntimeError through pybind11
+    raise LinemodLibraryError("linemod_b200 error %d: %s" % (rc, msg))
+
+
+class NativeDetector:
+    """Thin RAII wrapper over the lm_detector handle."""
+
+    def __init__(self, T, device=0):
+        L = load()
+        self._L = L
+        self.T = [int(t) for t in T]
+        self.levels = len(self.T)
+        arr = (ctypes.c_int * self.levels)(*self.T)
+        h = ctypes.c_void_p()
+        check(L.lm_create(int(device), self.levels, arr, ctypes.byref(h)))
+        self._h = h
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _i32(a):
+        return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+    def load_bank(self, packed, slots):
+        cb = np.ascontiguousarray(packed["class_begin"], np.int32)
+        tm = np.ascontiguousarray(packed["tmeta"], np.int32)
+        ft = np.ascontiguousarray(packed["feats"], np.int32)
+        check(self._L.lm_load_bank(self._h, len(cb) - 1, self._i32(cb), int(slots), self._i32(tm), self._i32(ft),
+                                   int(ft.shape[0])))
+
+    def select(self, class_indices=None, shard_index=0, shard_count=1):
+        if class_indices is None:
+            check(self._L.lm_select(self._h, None, -1, int(shard_index), int(shard_count)))
+        else:
+            a = np.ascontiguousarray(class_indices, np.int32)
+            check(self._L.lm_select(self._h, self._i32(a), int(a.shape[0]), int(shard_index), int(shard_count)))
+
+    def shard_range(self):
+        b, c = ctypes.c_int64(), ctypes.c_int64()
+        check(self._L.lm_shard_range(self._h, ctypes.byref(b), ctypes.byref(c)))
+        return b.value, c.value
+
+    def _frame_args(self, quantized):
+        qs = []
+        rows, cols = [], []
+        for lvl in quantized:
+            if len(lvl) != 2:
+                raise RuntimeError("sources.size() == modalities.size()")
+            rows.append(lvl[0].shape[0])
+            cols.append(lvl[0].shape[1])
+            for q in lvl:
+                if q.dtype != np.uint8 or q.ndim != 2 or q.shape != lvl[0].shape:
+                    raise TypeError("quantized images must be uint8 HxW, same size per level")
+                qs.append(np.ascontiguousarray(q))
+        if len(quantized) != self.levels:
+            raise RuntimeError("expected %d pyramid levels, got %d" % (self.levels, len(quantized)))
+        ptrs = (ctypes.POINTER(ctypes.c_uint8) * len(qs))(*[q.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) for q in qs])
+        r = (ctypes.c_int * len(rows))(*rows)
+        c = (ctypes.c_int * len(cols))(*cols)
+        return qs, ptrs, r, c
+
+    def upload_quantized(self, quantized):
+        qs, ptrs, r, c = self._frame_args(quantized)
+        check(self._L.lm_upload_quantized(self._h, ptrs, r, c))
+
+    def run(self, threshold):
+        check(self._L.lm_run(self._h, ctypes.c_float(threshold)))
+
+    def enqueue(self, threshold):
+        check(self._L.lm_enqueue(self._h, ctypes.c_float(threshold)))
+
+    def complete(self):
+        check(self._L.lm_complete(self._h))
+
+    def fetch_records(self):
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, RECORD_DTYPE)
+            n = ctypes.c_int64()
+            rc = self._L.lm_fetch_records(self._h, out.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(n))
+            if rc == LM_E_CAPACITY:
+                cap = int(n.value)
+                continue
+            check(rc)
+            return out[:n.value].copy()
+
+    def device_records(self):
+        p, c, cap = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+        check(self._L.lm_device_records(self._h, ctypes.byref(p), ctypes.byref(c), ctypes.byref(cap)))
+        return p.value, c.value, cap.value
+
+    def finish(self, records):
+        records = np.ascontiguousarray(records, RECORD_DTYPE)
+        cap = max(int(records.shape[0]), 1)
+        out = np.zeros(cap, MATCH_DTYPE)
+        n = ctypes.c_int64()
+        check(self._L.lm_finish(self._h, records.ctypes.data_as(ctypes.c_void_p), int(records.shape[0]),
+                                out.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(n)))
+        return out[:n.value].copy()
+
+    def match_quantized(self, quantized, threshold):
+        qs, ptrs, r, c = self._frame_args(quantized)
+        cap = 1 << 14
+        while True:
+            out = np.zeros(cap, MATCH_DTYPE)
+            n = ctypes.c_int64()
+            rc = self._L.lm_match_quantized(self._h, ptrs, r, c, ctypes.c_float(threshold),
+                                            out.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(n))
+            if rc == LM_E_CAPACITY:
+                cap = int(n.value)
+                continue
+            check(rc)
+            return out[:n.value].copy()
+
+    def linear_memories(self, level, modality, shape):
+        out = np.zeros(shape, np.uint8)
+        check(self._L.lm_debug_linear_memories(self._h, level, modality, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                               out.size))
+        return out
+
+    def counters(self):
+        a = (ctypes.c_int64 * 5)()
+        check(self._L.lm_counters(self._h, a))
+        keys = ["templates", "coarse_candidates", "scan_bytes", "refine_bytes", "kept"]
+        return dict(zip(keys, [int(v) for v in a]))
+
+    def set_timing(self, on):
+        check(self._L.lm_set_timing(self._h, 1 if on else 0))
+
+    def stage_times_us(self):
+        a = (ctypes.c_float * 5)()
+        check(self._L.lm_stage_times(self._h, a))
+        keys = ["linear_memories", "coarse_scan", "offsets", "refine", "total"]
+        return dict(zip(keys, [float(v) for v in a]))
+
+    def stream(self):
+        return self._L.lm_stream(self._h)
+
+    def launch_count(self):
+        return int(self._L.lm_launch_count(self._h))

@@ -1,0 +1,963 @@
+// linemod_b200.cu -- hand-written sm_100a kernels + C-ABI for the LINEMOD match hot path.
+//
+// Reference being replaced: linemodLevelup::Detector::match and everything below it
+// (linemodLevelup/linemodLevelup.cpp of meiqua/6DPose @ 619be57, "LL.cpp"):
+//   k_linear_memories  <- spread + computeResponseMaps + linearize      LL.cpp:1094-1243
+//   k_coarse_scan      <- similarity(_64) + addSimilarities(_64) + threshold loop
+//                                                                       LL.cpp:1284-1354, 1435-1534, 1836-1852
+//   k_scan_counts      <- candidates.push_back ordering (deterministic offsets)
+//   k_refine           <- similarityLocal(_64) + best-cell search + remove_if   LL.cpp:1366-1428, 1855-1938
+//   lm_finish (host)   <- std::sort + std::unique                       LL.cpp:1772-1774
+// Integer results (raw scores, x, y, template ids) are bit-exact; the float similarity is produced by
+// the same two IEEE operations as the reference ((raw * 100.f) / (4 * n)).
+//
+// No tensor cores: byte lookup / byte gather / 16-bit accumulate work.  No CPU fallback.
+
+#include "linemod_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+// --------------------------------------------------------------------------------------------
+// error plumbing
+// --------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(LM_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char* lm_last_error(void) { return g_err; }
+
+// --------------------------------------------------------------------------------------------
+// device-side structures
+// --------------------------------------------------------------------------------------------
+#define LM_SKIP_BIT 0x80000000u  // in fxy: feature is outside the image at its own level (LL.cpp:1330)
+
+struct LevelDev {
+  const uint8_t* lm;  // [M][8][T*T][plane] response bytes, contiguous, zero pad after the end
+  int T, rows, cols, Wd, Hd, plane;
+  int off;              // T/2 + (T%2 - 1), LL.cpp:1846/1862
+  uint32_t mod_stride;  // 8*T*T*plane
+};
+
+// Per (template, slot): x = first feature, y = feature count, z = template_positions P at the
+// slot's level (LL.cpp:1309), w = width | height << 16.
+typedef int4 TSlot;
+
+__device__ __forceinline__ float lm_score(int raw, int nfeat) {
+  // (raw_score * 100.f) / (4 * num_features), LL.cpp:1842 / 1918 -- two correctly rounded float ops
+  return __fdiv_rn(__fmul_rn((float)raw, 100.f), (float)(4 * nfeat));
+}
+
+// response of orientation o against spread mask v: the active SIMILARITY_LUT (LL.cpp:1121) is
+// 4 if bit o is set, else 1 if a neighbouring orientation bit is set, else 0 (checked against the
+// table in tests).
+__device__ __forceinline__ uint32_t lm_response(uint32_t v, int o) {
+  uint32_t hit = (v >> o) & 1u;
+  uint32_t nb = ((v >> ((o + 1) & 7)) | (v >> ((o + 7) & 7))) & 1u;
+  return hit ? 4u : nb;
+}
+
+// --------------------------------------------------------------------------------------------
+// K1: spread (OR over the forward TxT window) -> response maps -> linear memories
+// --------------------------------------------------------------------------------------------
+struct LinMemParams {
+  const uint8_t* q[LM_MAX_MODALITIES];  // quantized u8 rows x cols
+  uint8_t* lm;
+  int T, rows, cols, Wd, Hd, plane;
+  uint32_t mod_stride;
+};
+
+__global__ void __launch_bounds__(256) k_linear_memories(LinMemParams p) {
+  const int m = blockIdx.y;
+  const int T2 = p.T * p.T;
+  const int n = T2 * p.plane;
+  const uint8_t* __restrict__ q = p.q[m];
+  uint8_t* __restrict__ out = p.lm + (size_t)m * p.mod_stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int g = i / p.plane, pos = i - g * p.plane;
+    const int gy = g / p.T, gx = g - gy * p.T;
+    const int py = pos / p.Wd, px = pos - py * p.Wd;
+    const int y = py * p.T + gy, x = px * p.T + gx;
+    const int y1 = min(y + p.T, p.rows), x1 = min(x + p.T, p.cols);
+    uint32_t v = 0;
+    for (int yy = y; yy < y1; ++yy) {
+      const uint8_t* row = q + (size_t)yy * p.cols;
+      for (int xx = x; xx < x1; ++xx) v |= __ldg(row + xx);
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) out[(size_t)o * n + i] = (uint8_t)lm_response(v, o);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// K2: coarse similarity scan of one template per CTA over the lowest pyramid level
+// --------------------------------------------------------------------------------------------
+struct ScanParams {
+  LevelDev lv;
+  const TSlot* tslot;
+  const uint32_t* fbase;
+  const uint32_t* fxy;
+  const int32_t* work;  // template ids of this shard, in match order
+  int S, M, slot_low;
+  float threshold;
+  uint32_t* cand;  // [n_work][plane]: j | raw << 16, ascending j
+  int32_t* cnt;    // [n_work]
+};
+
+#define SCAN_FEAT_TILE 512
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  __syncthreads();  // protect s_warp reuse
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int t = lane < nw ? s_warp[lane] : 0;
+    int ti = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, ti, d);
+      if (lane >= d) ti += u;
+    }
+    if (lane < nw) s_warp[lane] = ti - t;
+    if (lane == 31) s_warp[32] = ti;
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[wid] + inc - v;
+}
+
+__global__ void __launch_bounds__(1024) k_coarse_scan(ScanParams p) {
+  __shared__ uint32_t s_base[SCAN_FEAT_TILE];
+  __shared__ int s_warp[33];
+  const int w = blockIdx.x;
+  const int g = p.work[w];
+  const int plane = p.lv.plane;
+  const uint32_t* __restrict__ lm32 = reinterpret_cast<const uint32_t*>(p.lv.lm);
+  uint32_t* __restrict__ cand = p.cand + (size_t)w * plane;
+
+  int nfeat = 0;
+  for (int m = 0; m < p.M; ++m) nfeat += p.tslot[(size_t)g * p.S + p.slot_low + m].y;
+
+  int emitted = 0;
+  for (int j0 = 0; j0 < plane; j0 += blockDim.x * 4) {
+    const int j = j0 + threadIdx.x * 4;
+    uint32_t s01 = 0, s23 = 0;  // u16 pairs: positions (j, j+1) and (j+2, j+3)
+    for (int m = 0; m < p.M; ++m) {
+      const TSlot ts = p.tslot[(size_t)g * p.S + p.slot_low + m];
+      const int P = ts.z;
+      // positions >= P stay zero ("dst zero elsewhere", LL.cpp:1314)
+      uint32_t pm = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pm |= (j + k < P) ? (0xFFu << (8 * k)) : 0u;
+      for (int f0 = 0; f0 < ts.y; f0 += SCAN_FEAT_TILE) {
+        const int nt = min(SCAN_FEAT_TILE, ts.y - f0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+          const uint32_t xy = p.fxy[ts.x + f0 + i];
+          s_base[i] = (xy & LM_SKIP_BIT) ? 0xFFFFFFFFu : p.fbase[ts.x + f0 + i];
+        }
+        __syncthreads();
+        if (pm) {
+          uint32_t a8 = 0;
+          int pend = 0;
+          for (int i = 0; i < nt; ++i) {
+            const uint32_t b = s_base[i];
+            if (b == 0xFFFFFFFFu) continue;
+            const uint32_t a = b + (uint32_t)j;
+            const uint32_t lo = __ldg(lm32 + (a >> 2));
+            const uint32_t hi = __ldg(lm32 + (a >> 2) + 1);
+            a8 += __funnelshift_r(lo, hi, (a & 3u) << 3) & pm;
+            if (++pend == 63) {  // 63 * 4 = 252 < 256: no carry between packed bytes
+              s01 += __byte_perm(a8, 0, 0x4140);
+              s23 += __byte_perm(a8, 0, 0x4342);
+              a8 = 0;
+              pend = 0;
+            }
+          }
+          s01 += __byte_perm(a8, 0, 0x4140);
+          s23 += __byte_perm(a8, 0, 0x4342);
+        }
+      }
+    }
+    // threshold (LL.cpp:1836-1852) + ordered emission
+    int raw[4] = {(int)(s01 & 0xFFFF), (int)(s01 >> 16), (int)(s23 & 0xFFFF), (int)(s23 >> 16)};
+    uint32_t pass = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (j + k < plane && lm_score(raw[k], nfeat) > p.threshold) pass |= 1u << k;
+    int total;
+    int rank = emitted + block_exclusive_scan(__popc(pass), s_warp, &total);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (pass & (1u << k)) cand[rank++] = (uint32_t)(j + k) | ((uint32_t)raw[k] << 16);
+    emitted += total;
+  }
+  if (threadIdx.x == 0) p.cnt[w] = emitted;
+}
+
+// --------------------------------------------------------------------------------------------
+// exclusive scan of the per-template candidate counts -> global candidate offsets (ordered)
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
+                                                     int32_t* __restrict__ total_out) {
+  __shared__ int s_warp[33];
+  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int b = threadIdx.x * per, e = min(b + per, n);
+  int sum = 0;
+  for (int i = b; i < e; ++i) sum += cnt[i];
+  int total;
+  int run = block_exclusive_scan(sum, s_warp, &total);
+  for (int i = b; i < e; ++i) {
+    off[i] = run;
+    run += cnt[i];
+  }
+  if (threadIdx.x == 0) {
+    off[n] = total;
+    *total_out = total;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// K3: local refinement, one warp per coarse candidate, all upper pyramid levels
+// --------------------------------------------------------------------------------------------
+struct RefineParams {
+  LevelDev lv[LM_MAX_LEVELS];
+  const TSlot* tslot;
+  const uint32_t* fbase;
+  const uint32_t* fxy;
+  const int32_t* work;
+  const int32_t* off;   // [n_work + 1]
+  const uint32_t* cand;  // [n_work][plane_low]
+  int n_work, L, S, M;
+  int work_begin;  // global offset of this shard in the selected sequence
+  float threshold;
+  lm_record* out;
+  int32_t out_cap;
+  unsigned long long* counters;  // [0] refinement feature-rows processed (x256 = bytes), [1] kept
+};
+
+__global__ void __launch_bounds__(256) k_refine(RefineParams p) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int total = min(p.off[p.n_work], p.out_cap);
+  const LevelDev low = p.lv[p.L - 1];
+  const int row = lane >> 1, half = lane & 1;
+  unsigned long long feats_done = 0, kept_count = 0;
+
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < total; c += nwarps) {
+    // template of candidate c: last w with off[w] <= c
+    int lo = 0, hi = p.n_work;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (p.off[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int w = lo;
+    const int g = p.work[w];
+    const uint32_t cj = p.cand[(size_t)w * low.plane + (c - p.off[w])];
+    const int j = cj & 0xFFFF;
+    int nfeat = 0;
+    for (int m = 0; m < p.M; ++m) nfeat += p.tslot[(size_t)g * p.S + (p.L - 1) * p.M + m].y;
+    int x = (j % low.Wd) * low.T + low.off;
+    int y = (j / low.Wd) * low.T + low.off;
+    float sim = lm_score((int)(cj >> 16), nfeat);
+    bool kept = true;
+
+    for (int l = p.L - 2; l >= 0 && kept; --l) {
+      const LevelDev lv = p.lv[l];
+      const uint32_t* __restrict__ lm32 = reinterpret_cast<const uint32_t*>(lv.lm);
+      const TSlot t0 = p.tslot[(size_t)g * p.S + l * p.M];
+      const int T = lv.T, border = 8 * T;
+      const int max_x = lv.cols - (t0.w & 0xFFFF) - border;
+      const int max_y = lv.rows - (int)((unsigned)t0.w >> 16) - border;
+      x = x * 2 + 1;
+      y = y * 2 + 1;
+      x = max(x, border); y = max(y, border);  // LL.cpp:1875-1880 (max first, then min)
+      x = min(x, max_x);  y = min(y, max_y);
+      const int cx = x / T - 8, cy = y / T - 8;  // truncating division, LL.cpp:1380-1381
+      const int ox = cx * T, oy = cy * T;
+      const int shift = cy * lv.Wd + cx + row * lv.Wd + half * 8;
+
+      uint32_t s01 = 0, s23 = 0, s45 = 0, s67 = 0;
+      int nf2 = 0;
+      for (int m = 0; m < p.M; ++m) {
+        const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
+        nf2 += ts.y;
+        uint32_t a8 = 0, b8 = 0;
+        int pend = 0;
+        for (int i = 0; i < ts.y; ++i) {
+          const uint32_t xy = __ldg(p.fxy + ts.x + i);
+          const int fx = (int)(xy & 0x7FFFu) + ox, fy = (int)((xy >> 16) & 0x7FFFu) + oy;
+          if (fx < 0 || fy < 0 || fx >= lv.cols || fy >= lv.rows) continue;  // LL.cpp:1394
+          const uint32_t a = __ldg(p.fbase + ts.x + i) + (uint32_t)shift;
+          const uint32_t w0 = __ldg(lm32 + (a >> 2));
+          const uint32_t w1 = __ldg(lm32 + (a >> 2) + 1);
+          const uint32_t w2 = __ldg(lm32 + (a >> 2) + 2);
+          const uint32_t sh = (a & 3u) << 3;
+          a8 += __funnelshift_r(w0, w1, sh);
+          b8 += __funnelshift_r(w1, w2, sh);
+          ++feats_done;
+          if (++pend == 63) {
+            s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
+            s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
+            a8 = b8 = 0;
+            pend = 0;
+          }
+        }
+        s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
+        s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
+      }
+      // best cell: strict > in row-major order == max raw, lowest cell index (LL.cpp:1910-1927)
+      const uint32_t v[8] = {s01 & 0xFFFF, s01 >> 16, s23 & 0xFFFF, s23 >> 16,
+                             s45 & 0xFFFF, s45 >> 16, s67 & 0xFFFF, s67 >> 16};
+      uint32_t key = 0;
+      const int cell0 = row * 16 + half * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) key = max(key, (v[k] << 8) | (uint32_t)(255 - (cell0 + k)));
+      key = __reduce_max_sync(0xffffffffu, key);
+      const int best_raw = (int)(key >> 8);
+      int br = -1, bc = -1;
+      if (best_raw > 0) {
+        const int cell = 255 - (int)(key & 255u);
+        br = cell >> 4;
+        bc = cell & 15;
+      }
+      sim = lm_score(best_raw, nf2);
+      x = (x / T - 8 + bc) * T + lv.off;  // LL.cpp:1930-1931
+      y = (y / T - 8 + br) * T + lv.off;
+      kept = !(sim < p.threshold);  // remove_if(similarity < threshold), LL.cpp:1935-1937
+    }
+    if (lane == 0) {
+      lm_record r;
+      r.x = x; r.y = y; r.similarity = sim;
+      r.work = kept ? (p.work_begin + w) : (-1 - (p.work_begin + w));
+      p.out[c] = r;
+      kept_count += kept;
+    }
+  }
+  if (lane == 0 && (feats_done | kept_count)) {
+    atomicAdd(p.counters + 0, feats_done);
+    atomicAdd(p.counters + 1, kept_count);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+struct LevelHost {
+  int T = 0, rows = 0, cols = 0, Wd = 0, Hd = 0, plane = 0;
+  uint8_t* d_q[LM_MAX_MODALITIES] = {nullptr, nullptr};
+  uint8_t* d_lm = nullptr;
+  size_t lm_bytes = 0;
+  uint32_t mod_stride = 0;
+};
+
+struct lm_detector {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int L = 0, M = LM_MAX_MODALITIES;
+  int T[LM_MAX_LEVELS] = {0};
+  LevelHost lv[LM_MAX_LEVELS];
+  bool have_frame = false, have_run = false;
+
+  // bank (host)
+  int n_classes = 0, S = 0, G = 0;
+  std::vector<int32_t> class_begin, tmeta, feats;
+  std::vector<uint8_t> feat_slot;  // slot (level*M+modality) of every feature
+  // bank (device), prepared for the current frame size
+  TSlot* d_tslot = nullptr;
+  uint32_t* d_fbase = nullptr;
+  uint32_t* d_fxy = nullptr;
+  int prep_rows[LM_MAX_LEVELS] = {0}, prep_cols[LM_MAX_LEVELS] = {0};
+  bool prepared = false;
+  std::vector<TSlot> h_tslot;
+  std::vector<uint8_t> feat_skip_low;
+
+  // selection / shard
+  std::vector<int32_t> sel;  // global template ids of the whole selected sequence
+  int64_t shard_begin = 0, shard_count = 0;
+  int shard_index = 0, shard_n = 1;
+  int32_t* d_work = nullptr;
+  bool work_dirty = true;
+
+  // per-run buffers
+  uint32_t* d_cand = nullptr; size_t cand_elems = 0;
+  int32_t* d_cnt = nullptr; int32_t* d_off = nullptr; size_t cnt_elems = 0;
+  int32_t* d_total = nullptr;
+  lm_record* d_rec = nullptr; int64_t rec_cap = 0;
+  unsigned long long* d_counters = nullptr;
+  int32_t* h_total = nullptr;  // pinned
+  unsigned long long* h_counters = nullptr;  // pinned
+  lm_record* h_rec = nullptr; int64_t h_rec_cap = 0;  // pinned staging
+  float last_threshold = 0.f;
+
+  bool timing = false;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int64_t launches = 0;
+  int64_t alg_scan_bytes = 0;
+  int sm_count = 148;
+};
+
+static void free_level(LevelHost& l) {
+  for (int m = 0; m < LM_MAX_MODALITIES; ++m) {
+    if (l.d_q[m]) cudaFree(l.d_q[m]);
+    l.d_q[m] = nullptr;
+  }
+  if (l.d_lm) cudaFree(l.d_lm);
+  l.d_lm = nullptr;
+}
+
+extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** out) {
+  if (!out) return fail(LM_E_INVALID, "out is null");
+  if (n_levels < 1 || n_levels > LM_MAX_LEVELS) return fail(LM_E_INVALID, "pyramid levels must be 1..%d", LM_MAX_LEVELS);
+  for (int l = 0; l < n_levels; ++l)
+    if (T[l] < 1 || T[l] > 16) return fail(LM_E_INVALID, "T[%d]=%d outside 1..16", l, T[l]);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(LM_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(LM_E_INVALID, "device %d out of range (have %d)", device, ndev);
+  CU(cudaSetDevice(device));
+  lm_detector* d = new lm_detector();
+  d->device = device;
+  d->L = n_levels;
+  for (int l = 0; l < n_levels; ++l) d->T[l] = T[l];
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  d->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  CU(cudaMalloc(&d->d_total, sizeof(int32_t)));
+  CU(cudaMalloc(&d->d_counters, 2 * sizeof(unsigned long long)));
+  CU(cudaMallocHost(&d->h_total, sizeof(int32_t)));
+  CU(cudaMallocHost(&d->h_counters, 2 * sizeof(unsigned long long)));
+  for (int i = 0; i < 5; ++i) CU(cudaEventCreate(&d->ev[i]));
+  *out = d;
+  return LM_OK;
+}
+
+extern "C" void lm_destroy(lm_detector* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  if (d->stream) cudaStreamSynchronize(d->stream);
+  for (int l = 0; l < LM_MAX_LEVELS; ++l) free_level(d->lv[l]);
+  cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_work);
+  cudaFree(d->d_cand); cudaFree(d->d_cnt); cudaFree(d->d_off); cudaFree(d->d_total);
+  cudaFree(d->d_rec); cudaFree(d->d_counters);
+  cudaFreeHost(d->h_total); cudaFreeHost(d->h_counters); cudaFreeHost(d->h_rec);
+  for (int i = 0; i < 5; ++i) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+  if (d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+}
+
+extern "C" void* lm_stream(lm_detector* d) { return d ? (void*)d->stream : nullptr; }
+extern "C" int64_t lm_launch_count(lm_detector* d) { return d ? d->launches : 0; }
+
+extern "C" int lm_load_bank(lm_detector* d, int n_classes, const int32_t* class_begin, int n_slots, const int32_t* tmeta,
+                            const int32_t* feats, int64_t n_feats) {
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  if (n_classes < 0 || !class_begin) return fail(LM_E_INVALID, "bad class table");
+  if (n_slots != d->L * d->M)
+    return fail(LM_E_INVALID, "template pyramids have %d templates, detector expects %d (levels x modalities)", n_slots,
+                d->L * d->M);
+  const int G = class_begin[n_classes];
+  if (class_begin[0] != 0) return fail(LM_E_INVALID, "class_begin[0] must be 0");
+  for (int c = 0; c < n_classes; ++c)
+    if (class_begin[c + 1] < class_begin[c]) return fail(LM_E_INVALID, "class_begin not monotone");
+  std::vector<uint8_t> slot_of((size_t)n_feats, 255);
+  for (int g = 0; g < G; ++g)
+    for (int s = 0; s < n_slots; ++s) {
+      const int32_t* m4 = tmeta + ((size_t)g * n_slots + s) * 4;
+      if (m4[2] < 0 || m4[3] < 0 || (int64_t)m4[2] + m4[3] > n_feats)
+        return fail(LM_E_INVALID, "template %d slot %d: feature range out of bounds", g, s);
+      if (m4[3] > 8191)  // CV_Assert(templ.features.size() <= 8191), LL.cpp:1291
+        return fail(LM_E_INVALID, "template %d slot %d has %d features (> 8191)", g, s, m4[3]);
+      if (m4[0] < 0 || m4[1] < 0 || m4[0] > 32767 || m4[1] > 32767)
+        return fail(LM_E_INVALID, "template %d slot %d: width/height outside 0..32767", g, s);
+      for (int i = 0; i < m4[3]; ++i) {
+        const int32_t* f = feats + ((size_t)m4[2] + i) * 3;
+        if (f[2] < 0 || f[2] > 7) return fail(LM_E_INVALID, "feature label %d outside [0,8)", f[2]);
+        if (f[0] < 0 || f[1] < 0 || f[0] > 32767 || f[1] > 32767)
+          return fail(LM_E_INVALID, "feature coordinate (%d,%d) outside 0..32767", f[0], f[1]);
+        slot_of[(size_t)m4[2] + i] = (uint8_t)s;
+      }
+    }
+  CU(cudaSetDevice(d->device));
+  d->n_classes = n_classes;
+  d->S = n_slots;
+  d->G = G;
+  d->class_begin.assign(class_begin, class_begin + n_classes + 1);
+  d->tmeta.assign(tmeta, tmeta + (size_t)G * n_slots * 4);
+  d->feats.assign(feats, feats + (size_t)n_feats * 3);
+  d->feat_slot.swap(slot_of);
+  cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy);
+  d->d_tslot = nullptr; d->d_fbase = nullptr; d->d_fxy = nullptr;
+  if (G > 0) CU(cudaMalloc(&d->d_tslot, sizeof(TSlot) * (size_t)G * n_slots));
+  if (n_feats > 0) {
+    CU(cudaMalloc(&d->d_fbase, sizeof(uint32_t) * (size_t)n_feats));
+    CU(cudaMalloc(&d->d_fxy, sizeof(uint32_t) * (size_t)n_feats));
+  }
+  d->prepared = false;
+  d->have_run = false;
+  // default selection: everything, one shard
+  return lm_select(d, nullptr, -1, 0, 1);
+}
+
+// Which accumulator width the reference would use and whether it would assert (LL.cpp:1813-1824).
+static int check_paths(const lm_detector* d, int g) {
+  for (int l = 0; l < d->L; ++l) {
+    int width = -1;
+    for (int m = 0; m < d->M; ++m) {
+      const int nf = d->tmeta[((size_t)g * d->S + l * d->M + m) * 4 + 3];
+      if (width <= 0) width = nf < 64 ? 1 : (nf < 8192 ? 2 : width);
+      if (width == 1 && nf > 63) return -1;  // CV_Assert(features.size() <= 63), LL.cpp:1457/1551
+    }
+  }
+  return 0;
+}
+
+extern "C" int lm_select(lm_detector* d, const int32_t* class_sel, int n_classes_sel, int shard_index, int shard_count) {
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return fail(LM_E_INVALID, "bad shard %d/%d", shard_index, shard_count);
+  std::vector<int32_t> sel;
+  if (n_classes_sel < 0) {
+    sel.resize(d->G);
+    for (int g = 0; g < d->G; ++g) sel[g] = g;
+  } else {
+    for (int i = 0; i < n_classes_sel; ++i) {
+      const int c = class_sel[i];
+      if (c < 0 || c >= d->n_classes) return fail(LM_E_INVALID, "class index %d out of range", c);
+      for (int g = d->class_begin[c]; g < d->class_begin[c + 1]; ++g) sel.push_back(g);
+    }
+  }
+  for (int32_t g : sel)
+    if (check_paths(d, g) != 0)
+      return fail(LM_E_INVALID, "template %d: first modality has < 64 features but another has > 63 "
+                                "(the reference asserts in similarity_64)", g);
+  // contiguous shard, balanced by lowest-level feature count (the coarse scan's work per template)
+  const int low = (d->L - 1) * d->M;
+  std::vector<int64_t> cum(sel.size() + 1, 0);
+  for (size_t i = 0; i < sel.size(); ++i) {
+    int64_t c = 1;
+    for (int m = 0; m < d->M; ++m) c += d->tmeta[((size_t)sel[i] * d->S + low + m) * 4 + 3];
+    cum[i + 1] = cum[i] + c;
+  }
+  auto cut = [&](int k) -> int64_t {
+    if (k <= 0) return 0;
+    if (k >= shard_count) return (int64_t)sel.size();
+    const int64_t target = cum.back() * k / shard_count;
+    return (int64_t)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+  };
+  d->sel.swap(sel);
+  d->shard_index = shard_index;
+  d->shard_n = shard_count;
+  d->shard_begin = cut(shard_index);
+  d->shard_count = cut(shard_index + 1) - d->shard_begin;
+  d->work_dirty = true;
+  d->have_run = false;
+  return LM_OK;
+}
+
+extern "C" int lm_shard_range(lm_detector* d, int64_t* begin, int64_t* count) {
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  if (begin) *begin = d->shard_begin;
+  if (count) *count = d->shard_count;
+  return LM_OK;
+}
+
+// Feature addresses depend on the frame size (Wd, Hd); recomputed when it changes.
+static int prepare_bank(lm_detector* d) {
+  bool same = d->prepared;
+  for (int l = 0; l < d->L && same; ++l) same = d->prep_rows[l] == d->lv[l].rows && d->prep_cols[l] == d->lv[l].cols;
+  if (same) return LM_OK;
+  const size_t nf = d->feat_slot.size();
+  std::vector<uint32_t> fbase(nf, 0), fxy(nf, 0);
+  for (size_t i = 0; i < nf; ++i) {
+    const int s = d->feat_slot[i];
+    if (s == 255) continue;  // feature not referenced by any template
+    const int l = s / d->M, m = s % d->M;
+    const LevelHost& lv = d->lv[l];
+    const int x = d->feats[3 * i], y = d->feats[3 * i + 1], lab = d->feats[3 * i + 2];
+    const int T = lv.T;
+    const uint64_t a = (uint64_t)m * lv.mod_stride + (uint64_t)lab * T * T * lv.plane +
+                       (uint64_t)((y % T) * T + (x % T)) * lv.plane + (uint64_t)(y / T) * lv.Wd + (x / T);
+    fbase[i] = (uint32_t)a;
+    uint32_t v = (uint32_t)x | ((uint32_t)y << 16);
+    if (x >= lv.cols || y >= lv.rows) v |= LM_SKIP_BIT;  // LL.cpp:1330
+    fxy[i] = v;
+  }
+  d->h_tslot.resize((size_t)d->G * d->S);
+  for (int g = 0; g < d->G; ++g)
+    for (int s = 0; s < d->S; ++s) {
+      const int32_t* m4 = &d->tmeta[((size_t)g * d->S + s) * 4];
+      const LevelHost& lv = d->lv[s / d->M];
+      const int wf = (m4[0] - 1) / lv.T + 1, hf = (m4[1] - 1) / lv.T + 1;  // LL.cpp:1299-1300
+      TSlot t;
+      t.x = m4[2];
+      t.y = m4[3];
+      t.z = (lv.Hd - hf) * lv.Wd + (lv.Wd - wf) + 1;  // LL.cpp:1309
+      t.w = (int)((uint32_t)m4[0] | ((uint32_t)m4[1] << 16));
+      d->h_tslot[(size_t)g * d->S + s] = t;
+    }
+  if (nf) {
+    CU(cudaMemcpyAsync(d->d_fbase, fbase.data(), nf * 4, cudaMemcpyHostToDevice, d->stream));
+    CU(cudaMemcpyAsync(d->d_fxy, fxy.data(), nf * 4, cudaMemcpyHostToDevice, d->stream));
+  }
+  if (d->G) CU(cudaMemcpyAsync(d->d_tslot, d->h_tslot.data(), sizeof(TSlot) * d->h_tslot.size(), cudaMemcpyHostToDevice, d->stream));
+  CU(cudaStreamSynchronize(d->stream));  // host vectors go out of scope
+  d->feat_skip_low.assign(nf, 0);
+  for (size_t i = 0; i < nf; ++i) d->feat_skip_low[i] = (fxy[i] & LM_SKIP_BIT) ? 1 : 0;
+  for (int l = 0; l < d->L; ++l) { d->prep_rows[l] = d->lv[l].rows; d->prep_cols[l] = d->lv[l].cols; }
+  d->prepared = true;
+  d->work_dirty = true;
+  return LM_OK;
+}
+
+static int prepare_work(lm_detector* d) {
+  if (!d->work_dirty) return LM_OK;
+  const int64_t n = d->shard_count;
+  cudaFree(d->d_work); d->d_work = nullptr;
+  if (n > 0) {
+    CU(cudaMalloc(&d->d_work, sizeof(int32_t) * (size_t)n));
+    CU(cudaMemcpyAsync(d->d_work, d->sel.data() + d->shard_begin, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+  }
+  if ((size_t)n + 1 > d->cnt_elems) {
+    cudaFree(d->d_cnt); cudaFree(d->d_off);
+    d->cnt_elems = (size_t)n + 1;
+    CU(cudaMalloc(&d->d_cnt, sizeof(int32_t) * d->cnt_elems));
+    CU(cudaMalloc(&d->d_off, sizeof(int32_t) * d->cnt_elems));
+  }
+  // algorithmic bytes of the coarse scan for this shard: sum features x positions
+  const int low = (d->L - 1) * d->M;
+  int64_t bytes = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int g = d->sel[d->shard_begin + i];
+    for (int m = 0; m < d->M; ++m) {
+      const TSlot& t = d->h_tslot[(size_t)g * d->S + low + m];
+      if (t.z <= 0) continue;
+      int live = 0;
+      for (int k = 0; k < t.y; ++k) live += d->feat_skip_low[(size_t)t.x + k] ? 0 : 1;
+      bytes += (int64_t)live * t.z;
+    }
+  }
+  d->alg_scan_bytes = bytes;
+  d->work_dirty = false;
+  return LM_OK;
+}
+
+extern "C" int lm_upload_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols) {
+  if (!d || !quantized || !rows || !cols) return fail(LM_E_INVALID, "null argument");
+  CU(cudaSetDevice(d->device));
+  for (int l = 0; l < d->L; ++l) {
+    const int T = d->T[l];
+    if (rows[l] <= 0 || cols[l] <= 0) return fail(LM_E_INVALID, "level %d: empty image", l);
+    if (rows[l] % T || cols[l] % T)  // CV_Assert LL.cpp:1217-1218
+      return fail(LM_E_INVALID, "level %d: %dx%d not a multiple of T=%d", l, cols[l], rows[l], T);
+    if (((int64_t)rows[l] * cols[l]) % 16)  // CV_Assert LL.cpp:1136
+      return fail(LM_E_INVALID, "level %d: rows*cols not a multiple of 16", l);
+    if (rows[l] > 32767 || cols[l] > 32767) return fail(LM_E_INVALID, "level %d: image side > 32767", l);
+  }
+  {
+    const int l = d->L - 1;
+    if ((int64_t)(rows[l] / d->T[l]) * (cols[l] / d->T[l]) > 65536)
+      return fail(LM_E_INVALID, "lowest level has more than 65536 sampled positions");
+  }
+  for (int l = 0; l < d->L; ++l) {
+    LevelHost& lv = d->lv[l];
+    if (lv.rows != rows[l] || lv.cols != cols[l] || lv.T != d->T[l]) {
+      free_level(lv);
+      lv.T = d->T[l]; lv.rows = rows[l]; lv.cols = cols[l];
+      lv.Wd = cols[l] / lv.T; lv.Hd = rows[l] / lv.T; lv.plane = lv.Wd * lv.Hd;
+      const size_t per_mod = (size_t)8 * lv.T * lv.T * lv.plane;
+      if (per_mod * d->M + lv.plane + 16 * (size_t)lv.Wd + 256 > 0xFFFFFFFFull) return fail(LM_E_INVALID, "level %d: linear memories exceed 4 GiB", l);
+      lv.mod_stride = (uint32_t)per_mod;
+      // slack: the coarse scan reads up to one plane past a feature's base, the 16x16 patch up to 16 rows
+      lv.lm_bytes = per_mod * d->M + (size_t)lv.plane + 16 * (size_t)lv.Wd + 256;
+      for (int m = 0; m < d->M; ++m) CU(cudaMalloc(&lv.d_q[m], (size_t)rows[l] * cols[l]));
+      CU(cudaMalloc(&lv.d_lm, lv.lm_bytes));
+      CU(cudaMemsetAsync(lv.d_lm, 0, lv.lm_bytes, d->stream));
+    }
+    for (int m = 0; m < d->M; ++m) {
+      const uint8_t* src = quantized[l * d->M + m];
+      if (!src) return fail(LM_E_INVALID, "quantized[%d] is null", l * d->M + m);
+      CU(cudaMemcpyAsync(lv.d_q[m], src, (size_t)rows[l] * cols[l], cudaMemcpyHostToDevice, d->stream));
+    }
+  }
+  CU(cudaStreamSynchronize(d->stream));  // caller's buffers are only borrowed for the call
+  d->have_frame = true;
+  d->have_run = false;
+  return LM_OK;
+}
+
+static LevelDev level_dev(const LevelHost& h) {
+  LevelDev v;
+  v.lm = h.d_lm; v.T = h.T; v.rows = h.rows; v.cols = h.cols; v.Wd = h.Wd; v.Hd = h.Hd; v.plane = h.plane;
+  v.off = h.T / 2 + (h.T % 2 - 1);
+  v.mod_stride = h.mod_stride;
+  return v;
+}
+
+// Enqueue every GPU stage of one frame on the detector's stream; no host synchronisation.
+static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
+  const int n_work = (int)d->shard_count;
+  const LevelHost& low = d->lv[d->L - 1];
+  cudaStream_t st = d->stream;
+  if (!refine_only) {
+    if (d->timing) CU(cudaEventRecord(d->ev[0], st));
+    // K1
+    for (int l = 0; l < d->L; ++l) {
+      const LevelHost& lv = d->lv[l];
+      LinMemParams p;
+      for (int m = 0; m < d->M; ++m) p.q[m] = lv.d_q[m];
+      p.lm = lv.d_lm; p.T = lv.T; p.rows = lv.rows; p.cols = lv.cols; p.Wd = lv.Wd; p.Hd = lv.Hd; p.plane = lv.plane;
+      p.mod_stride = lv.mod_stride;
+      const int n = lv.T * lv.T * lv.plane;
+      dim3 grid((unsigned)std::min((n + 255) / 256, d->sm_count * 8), (unsigned)d->M);
+      k_linear_memories<<<grid, 256, 0, st>>>(p);
+      ++d->launches;
+    }
+    if (d->timing) CU(cudaEventRecord(d->ev[1], st));
+    if (n_work > 0) {
+      ScanParams sp;
+      sp.lv = level_dev(low);
+      sp.tslot = d->d_tslot; sp.fbase = d->d_fbase; sp.fxy = d->d_fxy; sp.work = d->d_work;
+      sp.S = d->S; sp.M = d->M; sp.slot_low = (d->L - 1) * d->M;
+      sp.threshold = threshold;
+      sp.cand = d->d_cand; sp.cnt = d->d_cnt;
+      int bs = ((low.plane + 3) / 4 + 31) / 32 * 32;
+      bs = std::max(32, std::min(bs, 1024));
+      k_coarse_scan<<<n_work, bs, 0, st>>>(sp);
+      ++d->launches;
+    }
+    if (d->timing) CU(cudaEventRecord(d->ev[2], st));
+    k_scan_counts<<<1, 1024, 0, st>>>(d->d_cnt, d->d_off, n_work, d->d_total);
+    ++d->launches;
+    if (d->timing) CU(cudaEventRecord(d->ev[3], st));
+  }
+  CU(cudaMemsetAsync(d->d_counters, 0, 2 * sizeof(unsigned long long), st));
+  {
+    // persistent grid: the candidate total is read on the device (no host round trip)
+    RefineParams rp;
+    for (int l = 0; l < d->L; ++l) rp.lv[l] = level_dev(d->lv[l]);
+    rp.tslot = d->d_tslot; rp.fbase = d->d_fbase; rp.fxy = d->d_fxy; rp.work = d->d_work;
+    rp.off = d->d_off; rp.cand = d->d_cand;
+    rp.n_work = n_work; rp.L = d->L; rp.S = d->S; rp.M = d->M;
+    rp.work_begin = (int)d->shard_begin;
+    rp.threshold = threshold;
+    rp.out = d->d_rec; rp.out_cap = (int32_t)std::min<int64_t>(d->rec_cap, 0x7FFFFFFF);
+    rp.counters = d->d_counters;
+    k_refine<<<d->sm_count * 8, 256, 0, st>>>(rp);
+    ++d->launches;
+  }
+  if (d->timing) CU(cudaEventRecord(d->ev[4], st));
+  CU(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(d->h_counters, d->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  return LM_OK;
+}
+
+static int ensure_run_buffers(lm_detector* d) {
+  const int64_t n_work = d->shard_count;
+  const LevelHost& low = d->lv[d->L - 1];
+  const size_t need = (size_t)std::max<int64_t>(n_work, 1) * low.plane;
+  if (need > d->cand_elems) {
+    cudaFree(d->d_cand);
+    d->d_cand = nullptr;
+    d->cand_elems = need;
+    CU(cudaMalloc(&d->d_cand, sizeof(uint32_t) * need));
+  }
+  if (d->rec_cap == 0) {
+    d->rec_cap = 1 << 18;
+    CU(cudaMalloc(&d->d_rec, sizeof(lm_record) * (size_t)d->rec_cap));
+  }
+  return LM_OK;
+}
+
+extern "C" int lm_enqueue(lm_detector* d, float threshold) {
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  if (!d->have_frame) return fail(LM_E_STATE, "no frame uploaded");
+  if (d->S == 0) return fail(LM_E_STATE, "no template bank loaded");
+  CU(cudaSetDevice(d->device));
+  int rc = prepare_bank(d);
+  if (rc) return rc;
+  rc = prepare_work(d);
+  if (rc) return rc;
+  rc = ensure_run_buffers(d);
+  if (rc) return rc;
+  d->last_threshold = threshold;
+  return enqueue_stages(d, threshold, false);
+}
+
+extern "C" int lm_complete(lm_detector* d) {
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  CU(cudaSetDevice(d->device));
+  CU(cudaStreamSynchronize(d->stream));
+  CU(cudaGetLastError());
+  if ((int64_t)*d->h_total > d->rec_cap) {
+    // more coarse candidates than record slots: grow and redo the refinement stage only
+    cudaFree(d->d_rec);
+    d->d_rec = nullptr;
+    d->rec_cap = (int64_t)*d->h_total * 2;
+    CU(cudaMalloc(&d->d_rec, sizeof(lm_record) * (size_t)d->rec_cap));
+    int rc = enqueue_stages(d, d->last_threshold, true);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(d->stream));
+    CU(cudaGetLastError());
+  }
+  d->have_run = true;
+  return LM_OK;
+}
+
+extern "C" int lm_run(lm_detector* d, float threshold) {
+  int rc = lm_enqueue(d, threshold);
+  if (rc) return rc;
+  return lm_complete(d);
+}
+
+extern "C" int lm_device_records(lm_detector* d, void** d_records, void** d_count, int64_t* capacity) {
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  if (!d->have_run) return fail(LM_E_STATE, "lm_run has not been called");
+  if (d_records) *d_records = d->d_rec;
+  if (d_count) *d_count = d->d_total;
+  if (capacity) *capacity = d->rec_cap;
+  return LM_OK;
+}
+
+extern "C" int lm_fetch_records(lm_detector* d, lm_record* out, int64_t cap, int64_t* n_out) {
+  if (!d || !n_out) return fail(LM_E_INVALID, "null argument");
+  if (!d->have_run) return fail(LM_E_STATE, "lm_run has not been called");
+  CU(cudaSetDevice(d->device));
+  const int64_t n = *d->h_total;
+  *n_out = n;
+  if (n > cap) return fail(LM_E_CAPACITY, "%lld records, capacity %lld", (long long)n, (long long)cap);
+  if (n > 0) {
+    CU(cudaMemcpyAsync(out, d->d_rec, sizeof(lm_record) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+  }
+  return LM_OK;
+}
+
+namespace {
+struct HostMatch {  // LL.h:225-258 with class_index standing in for the class_id string
+  int x, y;
+  float similarity;
+  int class_index, template_id;
+  bool operator<(const HostMatch& o) const {
+    if (similarity != o.similarity) return similarity > o.similarity;
+    return template_id < o.template_id;
+  }
+  bool operator==(const HostMatch& o) const {
+    return x == o.x && y == o.y && similarity == o.similarity && class_index == o.class_index;
+  }
+};
+}  // namespace
+
+extern "C" int lm_finish(lm_detector* d, const lm_record* records, int64_t n, lm_match* out, int64_t cap, int64_t* n_out) {
+  if (!d || !n_out || (n > 0 && !records)) return fail(LM_E_INVALID, "null argument");
+  std::vector<int> class_of(d->G);
+  for (int c = 0; c < d->n_classes; ++c)
+    for (int g = d->class_begin[c]; g < d->class_begin[c + 1]; ++g) class_of[g] = c;
+  std::vector<HostMatch> v;
+  v.reserve((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    const lm_record& r = records[i];
+    if (r.work < 0) continue;
+    if ((size_t)r.work >= d->sel.size()) return fail(LM_E_INVALID, "record %lld: work index %d out of range", (long long)i, r.work);
+    const int g = d->sel[r.work];
+    const int c = class_of[g];
+    v.push_back(HostMatch{r.x, r.y, r.similarity, c, g - d->class_begin[c]});
+  }
+  std::sort(v.begin(), v.end());                      // LL.cpp:1772
+  v.erase(std::unique(v.begin(), v.end()), v.end());  // LL.cpp:1773-1774
+  *n_out = (int64_t)v.size();
+  if ((int64_t)v.size() > cap) return fail(LM_E_CAPACITY, "%zu matches, capacity %lld", v.size(), (long long)cap);
+  for (size_t i = 0; i < v.size(); ++i) {
+    out[i].x = v[i].x; out[i].y = v[i].y; out[i].similarity = v[i].similarity;
+    out[i].class_index = v[i].class_index; out[i].template_id = v[i].template_id;
+  }
+  return LM_OK;
+}
+
+extern "C" int lm_match_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols,
+                                  float threshold, lm_match* out, int64_t cap, int64_t* n_out) {
+  int rc = lm_upload_quantized(d, quantized, rows, cols);
+  if (rc) return rc;
+  rc = lm_run(d, threshold);
+  if (rc) return rc;
+  const int64_t n = *d->h_total;
+  if (n > d->h_rec_cap) {
+    cudaFreeHost(d->h_rec);
+    d->h_rec_cap = std::max<int64_t>(n * 2, 1 << 14);
+    CU(cudaMallocHost(&d->h_rec, sizeof(lm_record) * (size_t)d->h_rec_cap));
+  }
+  int64_t got = 0;
+  rc = lm_fetch_records(d, d->h_rec, d->h_rec_cap, &got);
+  if (rc) return rc;
+  return lm_finish(d, d->h_rec, got, out, cap, n_out);
+}
+
+extern "C" int lm_debug_linear_memories(lm_detector* d, int level, int modality, uint8_t* out, int64_t cap) {
+  if (!d || !out) return fail(LM_E_INVALID, "null argument");
+  if (!d->have_run) return fail(LM_E_STATE, "lm_run has not been called");
+  if (level < 0 || level >= d->L || modality < 0 || modality >= d->M) return fail(LM_E_INVALID, "bad level/modality");
+  const LevelHost& lv = d->lv[level];
+  if ((int64_t)lv.mod_stride > cap) return fail(LM_E_CAPACITY, "need %u bytes", lv.mod_stride);
+  CU(cudaSetDevice(d->device));
+  CU(cudaMemcpyAsync(out, lv.d_lm + (size_t)modality * lv.mod_stride, lv.mod_stride, cudaMemcpyDeviceToHost, d->stream));
+  CU(cudaStreamSynchronize(d->stream));
+  return LM_OK;
+}
+
+extern "C" int lm_counters(lm_detector* d, int64_t* out5) {
+  if (!d || !out5) return fail(LM_E_INVALID, "null argument");
+  if (!d->have_run) return fail(LM_E_STATE, "lm_run has not been called");
+  out5[0] = d->shard_count;
+  out5[1] = *d->h_total;
+  out5[2] = d->alg_scan_bytes;
+  out5[3] = (int64_t)d->h_counters[0] * 256;
+  out5[4] = (int64_t)d->h_counters[1];
+  return LM_OK;
+}
+
+extern "C" int lm_set_timing(lm_detector* d, int enable) {
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  d->timing = enable != 0;
+  return LM_OK;
+}
+
+extern "C" int lm_stage_times(lm_detector* d, float* out5) {
+  if (!d || !out5) return fail(LM_E_INVALID, "null argument");
+  if (!d->have_run || !d->timing) return fail(LM_E_STATE, "timing not enabled for the last run");
+  float ms;
+  for (int i = 0; i < 4; ++i) {
+    CU(cudaEventElapsedTime(&ms, d->ev[i], d->ev[i + 1]));
+    out5[i] = ms * 1000.f;
+  }
+  CU(cudaEventElapsedTime(&ms, d->ev[0], d->ev[4]));
+  out5[4] = ms * 1000.f;
+  return LM_OK;
+}

@@ -1,0 +1,170 @@
+"""Host-side mirror of the reference's Python surface (linemodLevelup/pybind11.cpp:7-35).
+
+`Detector`, `Match` and `poseRefine` keep the reference's names, argument order, keyword names and
+error behaviour; underneath, `Detector.match` calls the C-ABI library (CUDA, sm_100a) through
+ctypes.  The quantization front-end (cv2) and template extraction run on the host, as SURVEY.md
+section 8 rows a14 / f2 describe.
+"""
+import os
+
+import numpy as np
+
+from . import _lib, frontend
+from .bank import TemplateBank
+
+
+class Match:
+    """linemodLevelup::Match (pybind11.cpp:16-22): default-constructible, read/write attributes."""
+    __slots__ = ("x", "y", "similarity", "class_id", "template_id")
+
+    def __init__(self):
+        self.x = 0
+        self.y = 0
+        self.similarity = 0.0
+        self.class_id = ""
+        self.template_id = 0
+
+    def __repr__(self):
+        return "Match(x=%d, y=%d, similarity=%.4f, class_id=%r, template_id=%d)" % (
+            self.x, self.y, self.similarity, self.class_id, self.template_id)
+
+
+def _default_device():
+    for key in ("LINEMOD_B200_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(key)
+        if v is not None and v != "":
+            return int(v)
+    return 0
+
+
+class Detector:
+    """linemodLevelup::Detector as bound at pybind11.cpp:25-34.
+
+    Detector()                      -> 63 features, T = [5, 8]          (LL.cpp:1663-1672)
+    Detector(T)                     -> 63 features, T as given          (LL.cpp:1674-1682)
+    Detector(num_features, T)       -> ColorGradient(10, nf, 55), DepthNormal(2000, 50, nf, 2)  (LL.cpp:1684-1692)
+    """
+
+    def __init__(self, *args):
+        if len(args) == 0:
+            nf, T = 63, [5, 8]
+        elif len(args) == 1:
+            nf, T = 63, list(args[0])
+        elif len(args) == 2:
+            nf, T = int(args[0]), list(args[1])
+        else:
+            raise TypeError("Detector(): incompatible constructor arguments")
+        if not all(isinstance(t, (int, np.integer)) for t in T):
+            raise TypeError("Detector(): T must be a list of ints")
+        self.num_features = nf
+        self.T_at_level = [int(t) for t in T]
+        self.pyramid_levels = len(self.T_at_level)
+        self.bank = TemplateBank()
+        self._native = None
+        self._bank_dirty = True
+        self._class_order = []
+        self._selection = None
+        self.device = _default_device()
+        self.shard = (0, 1)  # (index, count): template shard matched by this process (multi-GPU)
+
+    # ---- template IO ----------------------------------------------------------------------
+    def readClasses(self, class_ids, format):
+        """Detector::readClasses, LL.cpp:2124-2134 (format is a printf pattern with one %s)."""
+        for cid in class_ids:
+            self.bank.read_class(format % cid, self.pyramid_levels)
+        self._bank_dirty = True
+
+    def writeClasses(self, format):
+        """Detector::writeClasses, LL.cpp:2136-2146."""
+        for cid in self.bank.class_ids():
+            self.bank.write_class(cid, format % cid, self.pyramid_levels)
+
+    def addTemplate(self, sources, class_id, object_mask):
+        """Detector::addTemplate, LL.cpp:1943-1975: returns the template id, or -1 on failure."""
+        from . import training
+        tid = training.add_template(self, sources, class_id, object_mask)
+        if tid >= 0:
+            self._bank_dirty = True
+        return tid
+
+    def getTemplates(self, class_id, template_id):
+        # The reference returns std::vector<Template>, a type pybind11.cpp never registers: calling it
+        # from Python raises TypeError.  Kept for surface parity.
+        raise TypeError("Unable to convert function return value to a Python type! (Template is not bound)")
+
+    def numTemplates(self, class_id=None):
+        return self.bank.num_templates(class_id)
+
+    def classIds(self):
+        return self.bank.class_ids()
+
+    # ---- matching -------------------------------------------------------------------------
+    def _ensure_native(self):
+        if self._native is None:
+            self._native = _lib.NativeDetector(self.T_at_level, self.device)
+            self._bank_dirty = True
+        if self._bank_dirty:
+            self._class_order = self.bank.class_ids()  # std::map iteration order
+            packed = self.bank.pack(self._class_order, self.pyramid_levels * 2)
+            self._native.load_bank(packed, self.pyramid_levels * 2)
+            self._bank_dirty = False
+            self._selection = None
+        return self._native
+
+    def _select(self, class_ids):
+        nat = self._ensure_native()
+        if not class_ids:
+            sel = None  # all classes, map order (LL.cpp:1753-1759)
+        else:
+            index = {c: i for i, c in enumerate(self._class_order)}
+            sel = [index[c] for c in class_ids if c in index]  # unknown ids are skipped (LL.cpp:1765-1767)
+        key = (None if sel is None else tuple(sel), self.shard)
+        if key != self._selection:
+            nat.select(sel, self.shard[0], self.shard[1])
+            self._selection = key
+        return nat
+
+    def quantize(self, sources, masks=None):
+        """The host front-end: list over levels of [color_labels, normal_labels] (u8)."""
+        return frontend.quantize_pyramid(sources, self.pyramid_levels, masks, self.num_features)
+
+    def match(self, sources, threshold, class_ids, masks=None):
+        """Detector::match (LL.cpp:1702-1777) -> list[Match], sorted, duplicates pruned.
+
+        As in the reference binding the declared default for `masks` is not convertible; every caller
+        passes masks=[] (linemod_and_levelup_test.py:324)."""
+        if masks is None:
+            raise TypeError("match(): incompatible function arguments (masks must be a list; pass masks=[])")
+        sources = [self._as_source(s, i) for i, s in enumerate(sources)]
+        quantized = self.quantize(sources, list(masks))
+        recs = self.match_quantized(quantized, threshold, class_ids)
+        return recs
+
+    def match_quantized(self, quantized, threshold, class_ids=()):
+        """Same as match() but starting from quantized label images (the accelerated path proper)."""
+        nat = self._select(list(class_ids))
+        out = nat.match_quantized(quantized, float(threshold))
+        return self._to_matches(out)
+
+    def _to_matches(self, out):
+        res = []
+        for r in out:
+            m = Match()
+            m.x = int(r["x"])
+            m.y = int(r["y"])
+            m.similarity = float(r["similarity"])
+            m.class_id = self._class_order[int(r["class_index"])]
+            m.template_id = int(r["template_id"])
+            res.append(m)
+        return res
+
+    @staticmethod
+    def _as_source(a, i):
+        a = np.asarray(a)
+        if i == 0:
+            if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+                raise TypeError("sources[0] must be a uint8 HxWx3 colour image")
+        else:
+            if a.dtype != np.uint16 or a.ndim != 2:
+                raise TypeError("sources[1] must be a uint16 HxW depth image (mm)")
+        return np.ascontiguousarray(a)

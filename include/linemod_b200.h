@@ -1,0 +1,131 @@
+/* linemod_b200.h -- C-ABI of the B200-native LINEMOD match + ICP pose-refinement path.
+ *
+ * This is the drop-in boundary: the entry points below are what a binding of the reference's
+ * `linemodLevelup_pybind` module (reference: linemodLevelup/pybind11.cpp:7-35) binds instead of the
+ * C++ classes `linemodLevelup::Detector` (linemodLevelup/linemodLevelup.h:264-375) and `poseRefine`
+ * (linemodLevelup.h:8-19).  Plain pointers and sizes only; no torch / OpenCV types.  All calls are
+ * blocking; one in-flight call per handle.  Every function returns 0 on success or a negative
+ * LM_E_* code, with a human-readable message available from lm_last_error() (thread-local).
+ * There is NO CPU fallback: without a CUDA device lm_create() fails.
+ *
+ * Citations "LL.cpp:n" = linemodLevelup/linemodLevelup.cpp of meiqua/6DPose @ 619be57.
+ */
+#ifndef LINEMOD_B200_H
+#define LINEMOD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM_OK 0
+#define LM_E_INVALID (-1) /* bad argument / a CV_Assert of the reference would fire */
+#define LM_E_CUDA (-2)    /* CUDA runtime error */
+#define LM_E_STATE (-3)   /* call order (no bank / no frame uploaded) */
+#define LM_E_CAPACITY (-4)
+
+#define LM_MAX_LEVELS 4
+#define LM_MAX_MODALITIES 2
+
+typedef struct lm_detector lm_detector; /* replaces linemodLevelup::Detector, LL.h:264 */
+
+/* One detection.  Replaces linemodLevelup::Match (LL.h:225-258); class_index indexes the class list
+ * given to lm_load_bank (the host shim maps it back to the class_id string). */
+typedef struct lm_match {
+  int32_t x, y;
+  float similarity;
+  int32_t class_index;
+  int32_t template_id;
+} lm_match;
+
+/* Pre-finish candidate record produced by the GPU stages, in the reference's pre-sort order
+ * (class order -> template_id -> ascending coarse cell; LL.cpp:1797-1939).  `work` is the index into
+ * the matched-template sequence of this call; negative (-1 - index) when the candidate fell below
+ * the threshold during refinement (LL.cpp:1935-1937).  16 bytes: the all-gather payload. */
+typedef struct lm_record {
+  int32_t x, y;
+  float similarity;
+  int32_t work;
+} lm_record;
+
+const char* lm_last_error(void);
+
+/* Detector(num_features, T) / Detector(T) / Detector(): LL.cpp:1663-1692.  `T` has n_levels entries
+ * (sampling step per pyramid level).  `device` is the CUDA ordinal. */
+int lm_create(int device, int n_levels, const int* T, lm_detector** out);
+void lm_destroy(lm_detector* d);
+
+/* Replace the template bank (class_templates, LL.h:361-362).  Flattened:
+ *   class_begin[n_classes+1]  global template ranges per class, in the caller's class order
+ *   tmeta[G][n_slots][4]      {width, height, feat_begin, feat_count}; n_slots = n_levels*2, slot =
+ *                             level*2 + modality (LL.cpp:1964)
+ *   feats[n_feats][3]         {x, y, label} (struct Feature, LL.h:23-34)
+ * Fails with LM_E_INVALID on label outside [0,8), negative coordinates, or > 8191 features in a
+ * template (CV_Assert LL.cpp:1291). */
+int lm_load_bank(lm_detector* d, int n_classes, const int32_t* class_begin, int n_slots, const int32_t* tmeta,
+                 const int32_t* feats, int64_t n_feats);
+
+/* Select which templates a call matches, in order: the concatenation of the given classes' template
+ * ranges (Detector::match's class_ids loop, LL.cpp:1753-1769), then the slice [shard_index/shard_count)
+ * of that sequence (contiguous, balanced by features x positions) -- the multi-GPU template shard.
+ * n_classes_sel < 0 selects all classes in bank order. */
+int lm_select(lm_detector* d, const int32_t* class_sel, int n_classes_sel, int shard_index, int shard_count);
+/* Global offset of this shard inside the selected sequence and its length. */
+int lm_shard_range(lm_detector* d, int64_t* begin, int64_t* count);
+
+/* Frame upload: quantized one-hot label images (output of QuantizedPyramid::quantize, LL.cpp:583-587,
+ * 882-886) for every (level, modality), host pointers, index level*2+modality; rows/cols per level.
+ * Fails where the reference asserts: rows%T, cols%T (LL.cpp:1217-1218), rows*cols%16 (LL.cpp:1136). */
+int lm_upload_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols);
+
+/* GPU stages on the uploaded frame: spread/response/linearize (LL.cpp:1094-1243), coarse similarity
+ * scan + threshold (LL.cpp:1284-1354, 1836-1852), local 16x16 refinement up the pyramid
+ * (LL.cpp:1366-1428, 1855-1938).  Leaves the ordered candidate records in device memory. */
+int lm_run(lm_detector* d, float threshold);
+/* lm_run split in two for pipelining: lm_enqueue issues every stage on the detector's stream and
+ * returns without synchronising; lm_complete waits, and re-runs the refinement stage if the record
+ * buffer was too small for the number of coarse candidates. */
+int lm_enqueue(lm_detector* d, float threshold);
+int lm_complete(lm_detector* d);
+
+/* Device-side results of the last lm_run: record array (lm_record[*], device pointer), device pointer
+ * to the int32 record count, and capacity.  For fused/peer consumers (NCCL all-gather, ICP hand-off). */
+int lm_device_records(lm_detector* d, void** d_records, void** d_count, int64_t* capacity);
+
+/* Copy the records of the last lm_run to the host (count first, then exactly that many). */
+int lm_fetch_records(lm_detector* d, lm_record* out, int64_t cap, int64_t* n_out);
+
+/* Host finisher: drop below-threshold records, map work -> (class_index, template_id) for the current
+ * selection (work indices are global in the selected sequence), then the reference's
+ * std::sort + std::unique (LL.cpp:1772-1774).  `records` may be the concatenation of all shards'
+ * records in shard order. */
+int lm_finish(lm_detector* d, const lm_record* records, int64_t n, lm_match* out, int64_t cap, int64_t* n_out);
+
+/* Convenience = lm_upload_quantized + lm_run + lm_fetch_records + lm_finish (single GPU):
+ * Detector::match after quantization. */
+int lm_match_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols,
+                       float threshold, lm_match* out, int64_t cap, int64_t* n_out);
+
+/* ---- introspection used by the parity tests and the benchmark ---- */
+/* Linear memories of (level, modality) of the last lm_run: [8][T*T][(cols/T)*(rows/T)] bytes. */
+int lm_debug_linear_memories(lm_detector* d, int level, int modality, uint8_t* out, int64_t cap);
+/* Counters of the last lm_run: [0] templates scanned, [1] coarse candidates, [2] algorithmic bytes of
+ * the coarse scan (sum over templates, modalities of features x positions),
+ * [3] algorithmic bytes of the refinement (features x 256 per refined candidate and level),
+ * [4] records kept after refinement. */
+int lm_counters(lm_detector* d, int64_t* out5);
+/* Per-stage device time of the last lm_run in microseconds (CUDA events on the detector's stream):
+ * [0] linear memories, [1] coarse scan, [2] candidate scan/offsets, [3] refinement, [4] total.
+ * Only valid after lm_set_timing(d, 1). */
+int lm_set_timing(lm_detector* d, int enable);
+int lm_stage_times(lm_detector* d, float* out5);
+/* The CUDA stream all work of this handle is issued on (cudaStream_t as void*). */
+void* lm_stream(lm_detector* d);
+/* Number of kernel launches issued by this handle since creation. */
+int64_t lm_launch_count(lm_detector* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
