@@ -19,7 +19,7 @@ RECORD_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("similarity", "<f4"), ("wo
 # every symbol include/linemod_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "lm_last_error", "lm_create", "lm_destroy", "lm_load_bank", "lm_select", "lm_shard_range",
-    "lm_upload_quantized", "lm_run", "lm_enqueue", "lm_complete", "lm_device_records", "lm_fetch_records",
+    "lm_upload_quantized", "lm_bind_quantized_device", "lm_run", "lm_enqueue", "lm_complete", "lm_device_records", "lm_fetch_records",
     "lm_finish", "lm_match_quantized", "lm_debug_linear_memories", "lm_counters", "lm_set_timing",
     "lm_stage_times", "lm_stream", "lm_launch_count",
 ]
@@ -52,6 +52,7 @@ def load():
     L.lm_select.argtypes = [vp, i32p, c_int, c_int, c_int]
     L.lm_shard_range.argtypes = [vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
     L.lm_upload_quantized.argtypes = [vp, u8pp, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
+    L.lm_bind_quantized_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
     L.lm_run.argtypes = [vp, c_f]
     L.lm_enqueue.argtypes = [vp, c_f]
     L.lm_complete.argtypes = [vp]
@@ -69,9 +70,7 @@ def load():
     L.lm_launch_count.argtypes = [vp]
     L.lm_launch_count.restype = c_i64
     for name in SYMBOLS:
-        fn = getattr(L, name)
-        if fn.restype is ctypes.c_int and name not in ("lm_last_error",):
-            fn.restype = c_int
+        getattr(L, name)  # AttributeError if the library does not export a declared symbol
     _lib = L
     return L
 
@@ -156,6 +155,13 @@ class NativeDetector:
         qs, ptrs, r, c = self._frame_args(quantized)
         check(self._L.lm_upload_quantized(self._h, ptrs, r, c))
 
+    def bind_quantized_device(self, ptrs, rows, cols):
+        """ptrs: device addresses (ints) index level*2+modality; rows/cols per level."""
+        p = (ctypes.c_void_p * len(ptrs))(*[int(x) for x in ptrs])
+        r = (ctypes.c_int * len(rows))(*[int(x) for x in rows])
+        c = (ctypes.c_int * len(cols))(*[int(x) for x in cols])
+        check(self._L.lm_bind_quantized_device(self._h, p, r, c))
+
     def run(self, threshold):
         check(self._L.lm_run(self._h, ctypes.c_float(threshold)))
 
@@ -217,8 +223,8 @@ class NativeDetector:
         keys = ["templates", "coarse_candidates", "scan_bytes", "refine_bytes", "kept"]
         return dict(zip(keys, [int(v) for v in a]))
 
-    def set_timing(self, on):
-        check(self._L.lm_set_timing(self._h, 1 if on else 0))
+    def set_timing(self, slots):
+        check(self._L.lm_set_timing(self._h, int(slots)))
 
     def stage_times_us(self):
         a = (ctypes.c_float * 5)()

@@ -371,7 +371,8 @@ __global__ void __launch_bounds__(256) k_refine(RefineParams p) {
 // --------------------------------------------------------------------------------------------
 struct LevelHost {
   int T = 0, rows = 0, cols = 0, Wd = 0, Hd = 0, plane = 0;
-  uint8_t* d_q[LM_MAX_MODALITIES] = {nullptr, nullptr};
+  uint8_t* d_q[LM_MAX_MODALITIES] = {nullptr, nullptr};           // owned upload buffers
+  const uint8_t* q_src[LM_MAX_MODALITIES] = {nullptr, nullptr};  // what K1 reads (owned or caller's device memory)
   uint8_t* d_lm = nullptr;
   size_t lm_bytes = 0;
   uint32_t mod_stride = 0;
@@ -417,7 +418,9 @@ struct lm_detector {
   float last_threshold = 0.f;
 
   bool timing = false;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> tev;  // timing slots x 5 events (ring)
+  int64_t timing_runs = 0;
+  cudaEvent_t* ev = nullptr;     // the slot used by the run being enqueued
   int64_t launches = 0;
   int64_t alg_scan_bytes = 0;
   int sm_count = 148;
@@ -427,6 +430,7 @@ static void free_level(LevelHost& l) {
   for (int m = 0; m < LM_MAX_MODALITIES; ++m) {
     if (l.d_q[m]) cudaFree(l.d_q[m]);
     l.d_q[m] = nullptr;
+    l.q_src[m] = nullptr;
   }
   if (l.d_lm) cudaFree(l.d_lm);
   l.d_lm = nullptr;
@@ -455,7 +459,6 @@ extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** o
   CU(cudaMalloc(&d->d_counters, 2 * sizeof(unsigned long long)));
   CU(cudaMallocHost(&d->h_total, sizeof(int32_t)));
   CU(cudaMallocHost(&d->h_counters, 2 * sizeof(unsigned long long)));
-  for (int i = 0; i < 5; ++i) CU(cudaEventCreate(&d->ev[i]));
   *out = d;
   return LM_OK;
 }
@@ -469,7 +472,7 @@ extern "C" void lm_destroy(lm_detector* d) {
   cudaFree(d->d_cand); cudaFree(d->d_cnt); cudaFree(d->d_off); cudaFree(d->d_total);
   cudaFree(d->d_rec); cudaFree(d->d_counters);
   cudaFreeHost(d->h_total); cudaFreeHost(d->h_counters); cudaFreeHost(d->h_rec);
-  for (int i = 0; i < 5; ++i) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+  for (cudaEvent_t e : d->tev) cudaEventDestroy(e);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
 }
@@ -572,11 +575,11 @@ extern "C" int lm_select(lm_detector* d, const int32_t* class_sel, int n_classes
     const int64_t target = cum.back() * k / shard_count;
     return (int64_t)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
   };
-  d->sel.swap(sel);
   d->shard_index = shard_index;
   d->shard_n = shard_count;
   d->shard_begin = cut(shard_index);
   d->shard_count = cut(shard_index + 1) - d->shard_begin;
+  d->sel.swap(sel);  // after the cuts: the lambda reads `sel`
   d->work_dirty = true;
   d->have_run = false;
   return LM_OK;
@@ -670,9 +673,7 @@ static int prepare_work(lm_detector* d) {
   return LM_OK;
 }
 
-extern "C" int lm_upload_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols) {
-  if (!d || !quantized || !rows || !cols) return fail(LM_E_INVALID, "null argument");
-  CU(cudaSetDevice(d->device));
+static int check_frame_dims(lm_detector* d, const int* rows, const int* cols) {
   for (int l = 0; l < d->L; ++l) {
     const int T = d->T[l];
     if (rows[l] <= 0 || cols[l] <= 0) return fail(LM_E_INVALID, "level %d: empty image", l);
@@ -682,11 +683,14 @@ extern "C" int lm_upload_quantized(lm_detector* d, const uint8_t* const* quantiz
       return fail(LM_E_INVALID, "level %d: rows*cols not a multiple of 16", l);
     if (rows[l] > 32767 || cols[l] > 32767) return fail(LM_E_INVALID, "level %d: image side > 32767", l);
   }
-  {
-    const int l = d->L - 1;
-    if ((int64_t)(rows[l] / d->T[l]) * (cols[l] / d->T[l]) > 65536)
-      return fail(LM_E_INVALID, "lowest level has more than 65536 sampled positions");
-  }
+  const int l = d->L - 1;
+  if ((int64_t)(rows[l] / d->T[l]) * (cols[l] / d->T[l]) > 65536)
+    return fail(LM_E_INVALID, "lowest level has more than 65536 sampled positions");
+  return LM_OK;
+}
+
+// (Re)allocate the per-level device buffers for a frame size.
+static int size_levels(lm_detector* d, const int* rows, const int* cols, bool need_upload_buffers) {
   for (int l = 0; l < d->L; ++l) {
     LevelHost& lv = d->lv[l];
     if (lv.rows != rows[l] || lv.cols != cols[l] || lv.T != d->T[l]) {
@@ -694,21 +698,55 @@ extern "C" int lm_upload_quantized(lm_detector* d, const uint8_t* const* quantiz
       lv.T = d->T[l]; lv.rows = rows[l]; lv.cols = cols[l];
       lv.Wd = cols[l] / lv.T; lv.Hd = rows[l] / lv.T; lv.plane = lv.Wd * lv.Hd;
       const size_t per_mod = (size_t)8 * lv.T * lv.T * lv.plane;
-      if (per_mod * d->M + lv.plane + 16 * (size_t)lv.Wd + 256 > 0xFFFFFFFFull) return fail(LM_E_INVALID, "level %d: linear memories exceed 4 GiB", l);
-      lv.mod_stride = (uint32_t)per_mod;
       // slack: the coarse scan reads up to one plane past a feature's base, the 16x16 patch up to 16 rows
-      lv.lm_bytes = per_mod * d->M + (size_t)lv.plane + 16 * (size_t)lv.Wd + 256;
-      for (int m = 0; m < d->M; ++m) CU(cudaMalloc(&lv.d_q[m], (size_t)rows[l] * cols[l]));
+      const size_t slack = (size_t)lv.plane + 16 * (size_t)lv.Wd + 256;
+      if (per_mod * d->M + slack > 0xFFFFFFFFull) return fail(LM_E_INVALID, "level %d: linear memories exceed 4 GiB", l);
+      lv.mod_stride = (uint32_t)per_mod;
+      lv.lm_bytes = per_mod * d->M + slack;
       CU(cudaMalloc(&lv.d_lm, lv.lm_bytes));
       CU(cudaMemsetAsync(lv.d_lm, 0, lv.lm_bytes, d->stream));
     }
+    if (need_upload_buffers)
+      for (int m = 0; m < d->M; ++m)
+        if (!lv.d_q[m]) CU(cudaMalloc(&lv.d_q[m], (size_t)rows[l] * cols[l]));
+  }
+  return LM_OK;
+}
+
+extern "C" int lm_upload_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols) {
+  if (!d || !quantized || !rows || !cols) return fail(LM_E_INVALID, "null argument");
+  CU(cudaSetDevice(d->device));
+  int rc = check_frame_dims(d, rows, cols);
+  if (rc) return rc;
+  rc = size_levels(d, rows, cols, true);
+  if (rc) return rc;
+  for (int l = 0; l < d->L; ++l) {
+    LevelHost& lv = d->lv[l];
     for (int m = 0; m < d->M; ++m) {
       const uint8_t* src = quantized[l * d->M + m];
       if (!src) return fail(LM_E_INVALID, "quantized[%d] is null", l * d->M + m);
       CU(cudaMemcpyAsync(lv.d_q[m], src, (size_t)rows[l] * cols[l], cudaMemcpyHostToDevice, d->stream));
+      lv.q_src[m] = lv.d_q[m];
     }
   }
   CU(cudaStreamSynchronize(d->stream));  // caller's buffers are only borrowed for the call
+  d->have_frame = true;
+  d->have_run = false;
+  return LM_OK;
+}
+
+extern "C" int lm_bind_quantized_device(lm_detector* d, const uint8_t* const* d_quantized, const int* rows, const int* cols) {
+  if (!d || !d_quantized || !rows || !cols) return fail(LM_E_INVALID, "null argument");
+  CU(cudaSetDevice(d->device));
+  int rc = check_frame_dims(d, rows, cols);
+  if (rc) return rc;
+  rc = size_levels(d, rows, cols, false);
+  if (rc) return rc;
+  for (int l = 0; l < d->L; ++l)
+    for (int m = 0; m < d->M; ++m) {
+      if (!d_quantized[l * d->M + m]) return fail(LM_E_INVALID, "d_quantized[%d] is null", l * d->M + m);
+      d->lv[l].q_src[m] = d_quantized[l * d->M + m];
+    }
   d->have_frame = true;
   d->have_run = false;
   return LM_OK;
@@ -727,13 +765,17 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
   const int n_work = (int)d->shard_count;
   const LevelHost& low = d->lv[d->L - 1];
   cudaStream_t st = d->stream;
+  if (d->timing && !refine_only) {
+    d->ev = d->tev.data() + 5 * (size_t)(d->timing_runs % (int64_t)(d->tev.size() / 5));
+    ++d->timing_runs;
+  }
   if (!refine_only) {
     if (d->timing) CU(cudaEventRecord(d->ev[0], st));
     // K1
     for (int l = 0; l < d->L; ++l) {
       const LevelHost& lv = d->lv[l];
       LinMemParams p;
-      for (int m = 0; m < d->M; ++m) p.q[m] = lv.d_q[m];
+      for (int m = 0; m < d->M; ++m) p.q[m] = lv.q_src[m];
       p.lm = lv.d_lm; p.T = lv.T; p.rows = lv.rows; p.cols = lv.cols; p.Wd = lv.Wd; p.Hd = lv.Hd; p.plane = lv.plane;
       p.mod_stride = lv.mod_stride;
       const int n = lv.T * lv.T * lv.plane;
@@ -943,21 +985,40 @@ extern "C" int lm_counters(lm_detector* d, int64_t* out5) {
   return LM_OK;
 }
 
-extern "C" int lm_set_timing(lm_detector* d, int enable) {
+extern "C" int lm_set_timing(lm_detector* d, int slots) {
   if (!d) return fail(LM_E_INVALID, "null detector");
-  d->timing = enable != 0;
+  CU(cudaSetDevice(d->device));
+  CU(cudaStreamSynchronize(d->stream));
+  for (cudaEvent_t e : d->tev) cudaEventDestroy(e);
+  d->tev.clear();
+  d->timing_runs = 0;
+  d->timing = slots > 0;
+  for (int i = 0; i < slots * 5; ++i) {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    d->tev.push_back(e);
+  }
   return LM_OK;
 }
 
 extern "C" int lm_stage_times(lm_detector* d, float* out5) {
   if (!d || !out5) return fail(LM_E_INVALID, "null argument");
-  if (!d->have_run || !d->timing) return fail(LM_E_STATE, "timing not enabled for the last run");
-  float ms;
-  for (int i = 0; i < 4; ++i) {
-    CU(cudaEventElapsedTime(&ms, d->ev[i], d->ev[i + 1]));
-    out5[i] = ms * 1000.f;
+  if (!d->timing || d->timing_runs == 0) return fail(LM_E_STATE, "timing not enabled / no run recorded");
+  CU(cudaSetDevice(d->device));
+  CU(cudaStreamSynchronize(d->stream));
+  const int64_t slots = (int64_t)d->tev.size() / 5;
+  const int64_t n = std::min<int64_t>(slots, d->timing_runs);
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int64_t k = 0; k < n; ++k) {
+    cudaEvent_t* ev = d->tev.data() + 5 * k;
+    float ms;
+    for (int i = 0; i < 4; ++i) {
+      CU(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      acc[i] += ms * 1000.0;
+    }
+    CU(cudaEventElapsedTime(&ms, ev[0], ev[4]));
+    acc[4] += ms * 1000.0;
   }
-  CU(cudaEventElapsedTime(&ms, d->ev[0], d->ev[4]));
-  out5[4] = ms * 1000.f;
+  for (int i = 0; i < 5; ++i) out5[i] = (float)(acc[i] / (double)n);
   return LM_OK;
 }

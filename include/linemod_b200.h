@@ -79,6 +79,10 @@ int lm_shard_range(lm_detector* d, int64_t* begin, int64_t* count);
  * Fails where the reference asserts: rows%T, cols%T (LL.cpp:1217-1218), rows*cols%16 (LL.cpp:1136). */
 int lm_upload_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols);
 
+/* Same, but the label images already live in device memory (borrowed: they must stay valid and
+ * unchanged until the stages enqueued on them have completed).  No copy is made. */
+int lm_bind_quantized_device(lm_detector* d, const uint8_t* const* d_quantized, const int* rows, const int* cols);
+
 /* GPU stages on the uploaded frame: spread/response/linearize (LL.cpp:1094-1243), coarse similarity
  * scan + threshold (LL.cpp:1284-1354, 1836-1852), local 16x16 refinement up the pyramid
  * (LL.cpp:1366-1428, 1855-1938).  Leaves the ordered candidate records in device memory. */
@@ -115,10 +119,11 @@ int lm_debug_linear_memories(lm_detector* d, int level, int modality, uint8_t* o
  * [3] algorithmic bytes of the refinement (features x 256 per refined candidate and level),
  * [4] records kept after refinement. */
 int lm_counters(lm_detector* d, int64_t* out5);
-/* Per-stage device time of the last lm_run in microseconds (CUDA events on the detector's stream):
- * [0] linear memories, [1] coarse scan, [2] candidate scan/offsets, [3] refinement, [4] total.
- * Only valid after lm_set_timing(d, 1). */
-int lm_set_timing(lm_detector* d, int enable);
+/* Per-stage device time in microseconds, from CUDA events recorded on the detector's stream around
+ * each stage: [0] linear memories, [1] coarse scan, [2] candidate offsets, [3] refinement, [4] total.
+ * lm_set_timing(d, slots) with slots > 0 enables it and keeps the last `slots` runs (0 disables);
+ * lm_stage_times synchronises and returns the mean over the recorded runs. */
+int lm_set_timing(lm_detector* d, int slots);
 int lm_stage_times(lm_detector* d, float* out5);
 /* The CUDA stream all work of this handle is issued on (cudaStream_t as void*). */
 void* lm_stream(lm_detector* d);
