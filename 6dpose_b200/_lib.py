@@ -14,12 +14,13 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liblinemod_b200.so")
 LM_OK, LM_E_INVALID, LM_E_CUDA, LM_E_STATE, LM_E_CAPACITY = 0, -1, -2, -3, -4
 
 MATCH_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("similarity", "<f4"), ("class_index", "<i4"), ("template_id", "<i4")])
-RECORD_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("similarity", "<f4"), ("work", "<i4")])
+RECORD_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2"), ("similarity", "<f4"), ("work", "<i4"), ("seq", "<i4")])
+HEADER_DTYPE = np.dtype([("count", "<i4"), ("coarse_candidates", "<i4"), ("capacity", "<i4"), ("shard", "<i4")])
 
 # every symbol include/linemod_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "lm_last_error", "lm_create", "lm_destroy", "lm_load_bank", "lm_select", "lm_shard_range",
-    "lm_upload_quantized", "lm_bind_quantized_device", "lm_run", "lm_enqueue", "lm_complete", "lm_device_records", "lm_fetch_records",
+    "lm_upload_quantized", "lm_bind_quantized_device", "lm_run", "lm_enqueue", "lm_complete", "lm_set_result_buffer", "lm_device_result", "lm_fetch_records",
     "lm_finish", "lm_match_quantized", "lm_debug_linear_memories", "lm_counters", "lm_set_timing",
     "lm_stage_times", "lm_stream", "lm_launch_count",
 ]
@@ -56,7 +57,8 @@ def load():
     L.lm_run.argtypes = [vp, c_f]
     L.lm_enqueue.argtypes = [vp, c_f]
     L.lm_complete.argtypes = [vp]
-    L.lm_device_records.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(c_i64)]
+    L.lm_set_result_buffer.argtypes = [vp, vp, c_i64]
+    L.lm_device_result.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(c_i64)]
     L.lm_fetch_records.argtypes = [vp, vp, c_i64, ctypes.POINTER(c_i64)]
     L.lm_finish.argtypes = [vp, vp, c_i64, vp, c_i64, ctypes.POINTER(c_i64)]
     L.lm_match_quantized.argtypes = [vp, u8pp, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_f, vp, c_i64,
@@ -183,10 +185,13 @@ class NativeDetector:
             check(rc)
             return out[:n.value].copy()
 
-    def device_records(self):
-        p, c, cap = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
-        check(self._L.lm_device_records(self._h, ctypes.byref(p), ctypes.byref(c), ctypes.byref(cap)))
-        return p.value, c.value, cap.value
+    def set_result_buffer(self, device_ptr, capacity_records):
+        check(self._L.lm_set_result_buffer(self._h, ctypes.c_void_p(device_ptr) if device_ptr else None, int(capacity_records)))
+
+    def device_result(self):
+        p, cap = ctypes.c_void_p(), ctypes.c_int64()
+        check(self._L.lm_device_result(self._h, ctypes.byref(p), ctypes.byref(cap)))
+        return p.value, cap.value
 
     def finish(self, records):
         records = np.ascontiguousarray(records, RECORD_DTYPE)

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(1024) k_coarse_scan(ScanParams p) {
 // exclusive scan of the per-template candidate counts -> global candidate offsets (ordered)
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
-                                                     int32_t* __restrict__ total_out) {
+                                                     lm_result_header* __restrict__ hdr, int capacity, int shard) {
   __shared__ int s_warp[33];
   const int per = (n + blockDim.x - 1) / blockDim.x;
   const int b = threadIdx.x * per, e = min(b + per, n);
@@ -239,7 +239,10 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
   }
   if (threadIdx.x == 0) {
     off[n] = total;
-    *total_out = total;
+    hdr->count = 0;  // k_refine appends kept records behind the header
+    hdr->coarse_candidates = total;
+    hdr->capacity = capacity;
+    hdr->shard = shard;
   }
 }
 
@@ -257,18 +260,19 @@ struct RefineParams {
   int n_work, L, S, M;
   int work_begin;  // global offset of this shard in the selected sequence
   float threshold;
-  lm_record* out;
-  int32_t out_cap;
-  unsigned long long* counters;  // [0] refinement feature-rows processed (x256 = bytes), [1] kept
+  lm_result_header* hdr;  // result block: header, then `capacity` records
+  int32_t capacity;
+  unsigned long long* counters;  // [0] refinement feature-rows processed (x256 = bytes)
 };
 
 __global__ void __launch_bounds__(256) k_refine(RefineParams p) {
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int total = min(p.off[p.n_work], p.out_cap);
+  const int total = p.off[p.n_work];
   const LevelDev low = p.lv[p.L - 1];
   const int row = lane >> 1, half = lane & 1;
-  unsigned long long feats_done = 0, kept_count = 0;
+  unsigned long long feats_done = 0;
+  lm_record* __restrict__ out = reinterpret_cast<lm_record*>(p.hdr + 1);
 
   for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < total; c += nwarps) {
     // template of candidate c: last w with off[w] <= c
@@ -352,18 +356,19 @@ __global__ void __launch_bounds__(256) k_refine(RefineParams p) {
       y = (y / T - 8 + br) * T + lv.off;
       kept = !(sim < p.threshold);  // remove_if(similarity < threshold), LL.cpp:1935-1937
     }
-    if (lane == 0) {
-      lm_record r;
-      r.x = x; r.y = y; r.similarity = sim;
-      r.work = kept ? (p.work_begin + w) : (-1 - (p.work_begin + w));
-      p.out[c] = r;
-      kept_count += kept;
+    if (lane == 0 && kept) {
+      // unordered append; (work, seq) restores the reference's pre-sort order on the host
+      const int slot = atomicAdd(&p.hdr->count, 1);
+      if (slot < p.capacity) {
+        lm_record r;
+        r.x = (int16_t)x; r.y = (int16_t)y; r.similarity = sim;
+        r.work = p.work_begin + w;
+        r.seq = c;
+        out[slot] = r;
+      }
     }
   }
-  if (lane == 0 && (feats_done | kept_count)) {
-    atomicAdd(p.counters + 0, feats_done);
-    atomicAdd(p.counters + 1, kept_count);
-  }
+  if (lane == 0 && feats_done) atomicAdd(p.counters + 0, feats_done);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -409,12 +414,13 @@ struct lm_detector {
   // per-run buffers
   uint32_t* d_cand = nullptr; size_t cand_elems = 0;
   int32_t* d_cnt = nullptr; int32_t* d_off = nullptr; size_t cnt_elems = 0;
-  int32_t* d_total = nullptr;
-  lm_record* d_rec = nullptr; int64_t rec_cap = 0;
+  // result block (device): lm_result_header + capacity records; internal unless the caller set one
+  lm_result_header* d_res = nullptr; int64_t res_cap = 0; bool res_external = false;
+  lm_result_header* d_res_own = nullptr; int64_t res_cap_own = 0;
   unsigned long long* d_counters = nullptr;
-  int32_t* h_total = nullptr;  // pinned
   unsigned long long* h_counters = nullptr;  // pinned
-  lm_record* h_rec = nullptr; int64_t h_rec_cap = 0;  // pinned staging
+  lm_result_header* h_res = nullptr; int64_t h_res_cap = 0;  // pinned staging: header + records
+  int64_t h_valid = 0;                                       // records already copied to h_res
   float last_threshold = 0.f;
 
   bool timing = false;
@@ -455,9 +461,7 @@ extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** o
   CU(cudaGetDeviceProperties(&prop, device));
   d->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-  CU(cudaMalloc(&d->d_total, sizeof(int32_t)));
   CU(cudaMalloc(&d->d_counters, 2 * sizeof(unsigned long long)));
-  CU(cudaMallocHost(&d->h_total, sizeof(int32_t)));
   CU(cudaMallocHost(&d->h_counters, 2 * sizeof(unsigned long long)));
   *out = d;
   return LM_OK;
@@ -469,9 +473,9 @@ extern "C" void lm_destroy(lm_detector* d) {
   if (d->stream) cudaStreamSynchronize(d->stream);
   for (int l = 0; l < LM_MAX_LEVELS; ++l) free_level(d->lv[l]);
   cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_work);
-  cudaFree(d->d_cand); cudaFree(d->d_cnt); cudaFree(d->d_off); cudaFree(d->d_total);
-  cudaFree(d->d_rec); cudaFree(d->d_counters);
-  cudaFreeHost(d->h_total); cudaFreeHost(d->h_counters); cudaFreeHost(d->h_rec);
+  cudaFree(d->d_cand); cudaFree(d->d_cnt); cudaFree(d->d_off);
+  cudaFree(d->d_res_own); cudaFree(d->d_counters);
+  cudaFreeHost(d->h_counters); cudaFreeHost(d->h_res);
   for (cudaEvent_t e : d->tev) cudaEventDestroy(e);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
@@ -797,11 +801,12 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[2], st));
-    k_scan_counts<<<1, 1024, 0, st>>>(d->d_cnt, d->d_off, n_work, d->d_total);
+    k_scan_counts<<<1, 1024, 0, st>>>(d->d_cnt, d->d_off, n_work, d->d_res, (int)d->res_cap, d->shard_index);
     ++d->launches;
     if (d->timing) CU(cudaEventRecord(d->ev[3], st));
   }
   CU(cudaMemsetAsync(d->d_counters, 0, 2 * sizeof(unsigned long long), st));
+  if (refine_only) CU(cudaMemsetAsync(&d->d_res->count, 0, sizeof(int32_t), st));
   {
     // persistent grid: the candidate total is read on the device (no host round trip)
     RefineParams rp;
@@ -811,14 +816,25 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     rp.n_work = n_work; rp.L = d->L; rp.S = d->S; rp.M = d->M;
     rp.work_begin = (int)d->shard_begin;
     rp.threshold = threshold;
-    rp.out = d->d_rec; rp.out_cap = (int32_t)std::min<int64_t>(d->rec_cap, 0x7FFFFFFF);
+    rp.hdr = d->d_res; rp.capacity = (int32_t)d->res_cap;
     rp.counters = d->d_counters;
     k_refine<<<d->sm_count * 8, 256, 0, st>>>(rp);
     ++d->launches;
   }
   if (d->timing) CU(cudaEventRecord(d->ev[4], st));
-  CU(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  return LM_OK;
+}
+
+// header + the first records in one copy; the common case needs no second round trip
+#define LM_FIRST_FETCH 4096
+
+static int enqueue_readback(lm_detector* d) {
+  cudaStream_t st = d->stream;
+  const int64_t first = std::min<int64_t>(d->res_cap, LM_FIRST_FETCH);
+  CU(cudaMemcpyAsync(d->h_res, d->d_res, sizeof(lm_result_header) + sizeof(lm_record) * (size_t)first,
+                     cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(d->h_counters, d->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  d->h_valid = first;
   return LM_OK;
 }
 
@@ -832,9 +848,19 @@ static int ensure_run_buffers(lm_detector* d) {
     d->cand_elems = need;
     CU(cudaMalloc(&d->d_cand, sizeof(uint32_t) * need));
   }
-  if (d->rec_cap == 0) {
-    d->rec_cap = 1 << 18;
-    CU(cudaMalloc(&d->d_rec, sizeof(lm_record) * (size_t)d->rec_cap));
+  if (!d->res_external) {
+    if (d->res_cap_own == 0) {
+      d->res_cap_own = 1 << 16;
+      CU(cudaMalloc(&d->d_res_own, sizeof(lm_result_header) + sizeof(lm_record) * (size_t)d->res_cap_own));
+    }
+    d->d_res = d->d_res_own;
+    d->res_cap = d->res_cap_own;
+  }
+  if (d->h_res_cap < d->res_cap) {
+    cudaFreeHost(d->h_res);
+    d->h_res = nullptr;
+    d->h_res_cap = d->res_cap;
+    CU(cudaMallocHost(&d->h_res, sizeof(lm_result_header) + sizeof(lm_record) * (size_t)d->h_res_cap));
   }
   return LM_OK;
 }
@@ -857,15 +883,24 @@ extern "C" int lm_enqueue(lm_detector* d, float threshold) {
 extern "C" int lm_complete(lm_detector* d) {
   if (!d) return fail(LM_E_INVALID, "null detector");
   CU(cudaSetDevice(d->device));
+  int rc = enqueue_readback(d);
+  if (rc) return rc;
   CU(cudaStreamSynchronize(d->stream));
   CU(cudaGetLastError());
-  if ((int64_t)*d->h_total > d->rec_cap) {
-    // more coarse candidates than record slots: grow and redo the refinement stage only
-    cudaFree(d->d_rec);
-    d->d_rec = nullptr;
-    d->rec_cap = (int64_t)*d->h_total * 2;
-    CU(cudaMalloc(&d->d_rec, sizeof(lm_record) * (size_t)d->rec_cap));
-    int rc = enqueue_stages(d, d->last_threshold, true);
+  if ((int64_t)d->h_res->count > d->res_cap) {
+    if (d->res_external)
+      return fail(LM_E_CAPACITY, "%d records kept, caller's result buffer holds %lld", d->h_res->count, (long long)d->res_cap);
+    // more kept records than slots: grow the internal block and redo the refinement stage only
+    cudaFree(d->d_res_own);
+    d->d_res_own = nullptr;
+    d->res_cap_own = (int64_t)d->h_res->count * 2;
+    CU(cudaMalloc(&d->d_res_own, sizeof(lm_result_header) + sizeof(lm_record) * (size_t)d->res_cap_own));
+    CU(cudaMemcpyAsync(d->d_res_own, d->h_res, sizeof(lm_result_header), cudaMemcpyHostToDevice, d->stream));
+    rc = ensure_run_buffers(d);
+    if (rc) return rc;
+    rc = enqueue_stages(d, d->last_threshold, true);
+    if (rc) return rc;
+    rc = enqueue_readback(d);
     if (rc) return rc;
     CU(cudaStreamSynchronize(d->stream));
     CU(cudaGetLastError());
@@ -880,25 +915,51 @@ extern "C" int lm_run(lm_detector* d, float threshold) {
   return lm_complete(d);
 }
 
-extern "C" int lm_device_records(lm_detector* d, void** d_records, void** d_count, int64_t* capacity) {
+extern "C" int lm_set_result_buffer(lm_detector* d, void* d_block, int64_t capacity_records) {
   if (!d) return fail(LM_E_INVALID, "null detector");
-  if (!d->have_run) return fail(LM_E_STATE, "lm_run has not been called");
-  if (d_records) *d_records = d->d_rec;
-  if (d_count) *d_count = d->d_total;
-  if (capacity) *capacity = d->rec_cap;
+  if (d_block && capacity_records < 1) return fail(LM_E_INVALID, "capacity must be >= 1");
+  if (capacity_records > 0x7FFFFFFF) return fail(LM_E_INVALID, "capacity too large");
+  CU(cudaSetDevice(d->device));
+  CU(cudaStreamSynchronize(d->stream));
+  d->res_external = d_block != nullptr;
+  if (d->res_external) {
+    d->d_res = (lm_result_header*)d_block;
+    d->res_cap = capacity_records;
+  }
+  d->have_run = false;
   return LM_OK;
+}
+
+extern "C" int lm_device_result(lm_detector* d, void** d_block, int64_t* capacity_records) {
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  if (!d->d_res) return fail(LM_E_STATE, "no result block yet (call lm_enqueue / lm_run first)");
+  if (d_block) *d_block = d->d_res;
+  if (capacity_records) *capacity_records = d->res_cap;
+  return LM_OK;
+}
+
+static bool record_order(const lm_record& a, const lm_record& b) {
+  if (a.work != b.work) return a.work < b.work;
+  return a.seq < b.seq;
 }
 
 extern "C" int lm_fetch_records(lm_detector* d, lm_record* out, int64_t cap, int64_t* n_out) {
   if (!d || !n_out) return fail(LM_E_INVALID, "null argument");
   if (!d->have_run) return fail(LM_E_STATE, "lm_run has not been called");
   CU(cudaSetDevice(d->device));
-  const int64_t n = *d->h_total;
+  const int64_t n = d->h_res->count;
   *n_out = n;
   if (n > cap) return fail(LM_E_CAPACITY, "%lld records, capacity %lld", (long long)n, (long long)cap);
-  if (n > 0) {
-    CU(cudaMemcpyAsync(out, d->d_rec, sizeof(lm_record) * (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+  lm_record* h = reinterpret_cast<lm_record*>(d->h_res + 1);
+  if (n > d->h_valid) {  // the rest, beyond the first-fetch window
+    CU(cudaMemcpyAsync(h + d->h_valid, reinterpret_cast<lm_record*>(d->d_res + 1) + d->h_valid,
+                       sizeof(lm_record) * (size_t)(n - d->h_valid), cudaMemcpyDeviceToHost, d->stream));
     CU(cudaStreamSynchronize(d->stream));
+    d->h_valid = n;
+  }
+  if (n > 0) {
+    memcpy(out, h, sizeof(lm_record) * (size_t)n);
+    std::sort(out, out + n, record_order);  // the reference's pre-sort order
   }
   return LM_OK;
 }
@@ -923,12 +984,14 @@ extern "C" int lm_finish(lm_detector* d, const lm_record* records, int64_t n, lm
   std::vector<int> class_of(d->G);
   for (int c = 0; c < d->n_classes; ++c)
     for (int g = d->class_begin[c]; g < d->class_begin[c + 1]; ++g) class_of[g] = c;
+  std::vector<lm_record> rec(records, records + n);
+  std::sort(rec.begin(), rec.end(), record_order);  // class order -> template_id -> coarse cell (LL.cpp:1797-1939)
   std::vector<HostMatch> v;
   v.reserve((size_t)n);
   for (int64_t i = 0; i < n; ++i) {
-    const lm_record& r = records[i];
-    if (r.work < 0) continue;
-    if ((size_t)r.work >= d->sel.size()) return fail(LM_E_INVALID, "record %lld: work index %d out of range", (long long)i, r.work);
+    const lm_record& r = rec[i];
+    if (r.work < 0 || (size_t)r.work >= d->sel.size())
+      return fail(LM_E_INVALID, "record %lld: work index %d out of range", (long long)i, r.work);
     const int g = d->sel[r.work];
     const int c = class_of[g];
     v.push_back(HostMatch{r.x, r.y, r.similarity, c, g - d->class_begin[c]});
@@ -950,16 +1013,12 @@ extern "C" int lm_match_quantized(lm_detector* d, const uint8_t* const* quantize
   if (rc) return rc;
   rc = lm_run(d, threshold);
   if (rc) return rc;
-  const int64_t n = *d->h_total;
-  if (n > d->h_rec_cap) {
-    cudaFreeHost(d->h_rec);
-    d->h_rec_cap = std::max<int64_t>(n * 2, 1 << 14);
-    CU(cudaMallocHost(&d->h_rec, sizeof(lm_record) * (size_t)d->h_rec_cap));
-  }
+  const int64_t n = d->h_res->count;
+  std::vector<lm_record> rec((size_t)n);
   int64_t got = 0;
-  rc = lm_fetch_records(d, d->h_rec, d->h_rec_cap, &got);
+  rc = lm_fetch_records(d, rec.data(), n, &got);
   if (rc) return rc;
-  return lm_finish(d, d->h_rec, got, out, cap, n_out);
+  return lm_finish(d, rec.data(), got, out, cap, n_out);
 }
 
 extern "C" int lm_debug_linear_memories(lm_detector* d, int level, int modality, uint8_t* out, int64_t cap) {
@@ -978,10 +1037,10 @@ extern "C" int lm_counters(lm_detector* d, int64_t* out5) {
   if (!d || !out5) return fail(LM_E_INVALID, "null argument");
   if (!d->have_run) return fail(LM_E_STATE, "lm_run has not been called");
   out5[0] = d->shard_count;
-  out5[1] = *d->h_total;
+  out5[1] = d->h_res->coarse_candidates;
   out5[2] = d->alg_scan_bytes;
   out5[3] = (int64_t)d->h_counters[0] * 256;
-  out5[4] = (int64_t)d->h_counters[1];
+  out5[4] = d->h_res->count;
   return LM_OK;
 }
 

@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the LINEMOD match hot path (BASELINE.json: frames/sec @640x480 vs template-bank size).
+
+  python bench.py --gpus N --steps K --warmup W              our CUDA path
+  python bench.py --impl reference --gpus N --steps K ...    the reference's CPU algorithm on the host cores
+
+Workload (configs[1] of BASELINE.json): one object, 3115 templates (89 views x 35 variants), 150 features
+per modality at level 0 / 75 at level 1, T = [4, 8], 640x480 frames, threshold 75 (the caller's value,
+linemod_and_levelup_test.py:324).  No datasets exist offline: bank and frames are synthetic
+(6dpose_b200/synth.py), frames are generated as quantized label images with the fixture frame's
+statistics and 8 planted templates each.  A "step" = Detector::match of one frame after quantization
+(the cv2 quantization front-end is upstream of the accelerated path and identical for both arms).
+
+value  = frames/s with the frame ring resident in HBM, steps enqueued back to back on the detector's
+         stream, timed with CUDA events on that stream (max over ranks).
+e2e    = frames/s through the C-ABI call a binding makes (lm_match_quantized): label images in pinned host
+         memory -> H2D -> stages -> D2H of the kept records -> host finisher (sort/unique), one blocking
+         call per frame.
+N > 1  : the template bank is sharded over the ranks (strong scaling), every rank sees every frame, the
+         per-rank result blocks are all-gathered (NCCL) every step.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--templates", type=int, default=3115)
+    ap.add_argument("--features", type=int, default=150)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--threshold", type=float, default=75.0)
+    ap.add_argument("--ring", type=int, default=176, help="distinct frames cycled through (176 x 768 KB > 126 MB L2)")
+    ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the same workload timed for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=1234)
+    return ap.parse_args()
+
+
+T_PYR = [4, 8]
+
+
+def make_workload(args, n_frames):
+    synth = importlib.import_module("6dpose_b200.synth")
+    bank = synth.synth_bank(args.templates, num_features=args.features, levels=2, seed=args.seed, variants=35)
+    frames = []
+    for i in range(n_frames):
+        q, _ = synth.synth_frame(args.width, args.height, levels=2, seed=1000 + i, bank=bank, plant=8, T=T_PYR)
+        frames.append(q)
+    return bank, frames
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_fps(args, bank, frames, n_frames, threads):
+    """The reference's CPU algorithm (oracle port, or oracle/_ref when built) on the host cores."""
+    from oracle import oracle
+    packed = bank.pack(bank.class_ids(), 4)
+    kind = "port"
+    run = lambda q: oracle.match(q, T_PYR, packed, args.threshold, n_threads=threads)
+    try:
+        from oracle import ref as oref
+        if oref.available():
+            kind = "reference"
+            run = lambda q: oref.match(q, T_PYR, packed, args.threshold, n_threads=threads)
+    except ImportError:
+        pass
+    run(frames[0])  # warm-up (page in, thread pool)
+    t0 = time.perf_counter()
+    n = 0
+    for i in range(n_frames):
+        r = run(frames[i % len(frames)])
+        n += 1
+    dt = time.perf_counter() - t0
+    return n / dt, kind, dt, len(r)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_frames = min(max(args.steps + args.warmup, 1), 64)
+    bank, frames = make_workload(args, min(n_frames, 8))
+    from oracle import oracle
+    packed = bank.pack(bank.class_ids(), 4)
+    kind = "port"
+    fn = oracle.match
+    try:
+        from oracle import ref as oref
+        if oref.available():
+            kind, fn = "reference", oref.match
+    except ImportError:
+        pass
+    for i in range(args.warmup):
+        fn(frames[i % len(frames)], T_PYR, packed, args.threshold, n_threads=threads)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        fn(frames[i % len(frames)], T_PYR, packed, args.threshold, n_threads=threads)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    out = {
+        "impl": "reference", "metric": "frames/sec @640x480, 3115-template bank, Detector::match after quantization",
+        "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u8/u16", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                         "sample": "%d full frames of the same workload, OpenMP over templates" % args.steps},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def workload_config(args, n):
+    return {"workload": "obj_01-like synthetic bank, %d templates (89 views x 35 variants), %d features/modality at L0, "
+                        "T=[4,8], %dx%d quantized RGB-D frames, threshold %g, 8 planted templates per frame"
+                        % (args.templates, args.features, args.width, args.height, args.threshold),
+            "templates": args.templates, "frame": [args.width, args.height], "threshold": args.threshold,
+            "parallelism": "template-shard x%d" % n,
+            "l2": "ring of %d distinct frames (%.0f MB of label images > 126 MB L2); bank and linear memories are "
+                  "L2-resident by design" % (args.ring, args.ring * (args.width * args.height * 2 * 1.25) / 1e6)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    lib = importlib.import_module("6dpose_b200._lib")
+    bank, frames = make_workload(args, args.ring)
+    packed = bank.pack(bank.class_ids(), 4)
+    nat = lib.NativeDetector(T_PYR, device=local)
+    nat.load_bank(packed, 4)
+    nat.select(None, rank, world)
+
+    # frame ring resident in HBM (torch owns the memory; the library borrows the pointers)
+    rows = [args.height, args.height // 2]
+    cols = [args.width, args.width // 2]
+    ring = []
+    for q in frames:
+        ts = [torch.from_numpy(np.ascontiguousarray(q[l][m])).cuda() for l in range(2) for m in range(2)]
+        ring.append((ts, [t.data_ptr() for t in ts]))
+    stream = torch.cuda.ExternalStream(nat.stream(), device=local)
+
+    # result block: torch-owned so that it can be the NCCL all-gather send buffer
+    cap = 16384
+    blk_bytes = 16 + 16 * cap
+    res = torch.zeros(blk_bytes, dtype=torch.uint8, device="cuda")
+    nat.set_result_buffer(res.data_ptr(), cap)
+    gathered = torch.zeros(world * blk_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def step(i):
+        ts, ptrs = ring[i % len(ring)]
+        nat.bind_quantized_device(ptrs, rows, cols)
+        nat.enqueue(args.threshold)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, res)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    nat.complete()
+    barrier()
+
+    # ---- timed region: K steps, device resident --------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(stream)
+    nat.complete()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = nat.launch_count() - launches0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device="cuda")
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    fps = args.steps / (ms / 1e3)
+    counters = nat.counters()
+
+    # ---- per-kernel durations over K more steps (CUDA events on the launching stream) ------------
+    nat.set_timing(min(args.steps, 256))
+    for i in range(min(args.steps, 256)):
+        step(args.warmup + i)
+    nat.complete()
+    stage = nat.stage_times_us()
+    nat.set_timing(0)
+    barrier()
+
+    # ---- e2e: host buffers through the C-ABI match call ------------------------------------------
+    nat.set_result_buffer(0, 0)
+    host_frames = []
+    for q in frames[:min(len(frames), 64)]:
+        hq = [[torch.from_numpy(np.ascontiguousarray(q[l][m])).pin_memory().numpy() for m in range(2)] for l in range(2)]
+        host_frames.append(hq)
+    h2d = sum(a.nbytes for lvl in host_frames[0] for a in lvl)
+
+    def e2e_step(i):
+        q = host_frames[i % len(host_frames)]
+        if world == 1:
+            return nat.match_quantized(q, args.threshold)
+        nat.upload_quantized(q)
+        nat.run(args.threshold)
+        rec = nat.fetch_records()
+        allrec = [None] * world
+        dist.all_gather_object(allrec, rec)
+        if rank == 0:
+            return nat.finish(np.concatenate(allrec))
+        return rec
+
+    for i in range(3):
+        out = e2e_step(i)
+    barrier()
+    n_e2e = min(args.steps, 100)
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(n_e2e):
+        out = e2e_step(i)
+        d2h += 16 + 16 * nat.counters()["kept"]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_fps = n_e2e / dt
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+    scan_us, refine_us = stage["coarse_scan"], stage["refine"]
+    scan_gbs = counters["scan_bytes"] / (scan_us * 1e-6) / 1e9 if scan_us > 0 else 0.0
+    refine_gbs = counters["refine_bytes"] / (refine_us * 1e-6) / 1e9 if refine_us > 0 else 0.0
+    dominant = "k_coarse_scan" if scan_us >= refine_us else "k_refine"
+    ach = scan_gbs if dominant == "k_coarse_scan" else refine_gbs
+    roofline = {
+        "bound": "hbm", "kernel": dominant, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+        "traffic": None, "peak_source": peak_src,
+        "note": "effective bandwidth over ALGORITHMIC bytes (one response byte per feature x position; SURVEY 8d) "
+                "of this rank's shard; the working set is L2/L1-resident, DRAM traffic is far lower",
+        "kernels": {
+            "k_linear_memories": {"us": stage["linear_memories"]},
+            "k_coarse_scan": {"us": scan_us, "alg_bytes": counters["scan_bytes"], "gbs": scan_gbs, "frac": scan_gbs / hbm},
+            "k_scan_counts": {"us": stage["offsets"]},
+            "k_refine": {"us": refine_us, "alg_bytes": counters["refine_bytes"], "gbs": refine_gbs, "frac": refine_gbs / hbm},
+            "stages_total_us": stage["total"],
+        },
+    }
+    out = {
+        "metric": "frames/sec @640x480, 3115-template bank, Detector::match after quantization",
+        "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u8/u16", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // max(n_e2e, 1),
+                "steps": n_e2e, "api": "lm_match_quantized (C-ABI), pinned host label images -> matches"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "counters": counters,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        v, kind, dt_cpu, nm = cpu_reference_fps(args, bank, frames, args.cpu_frames, threads)
+        out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": threads, "kind": kind,
+                               "sample": "%d full frames of the same workload in %.1f s, OpenMP over templates" % (args.cpu_frames, dt_cpu)}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,15 +39,25 @@ typedef struct lm_match {
   int32_t template_id;
 } lm_match;
 
-/* Pre-finish candidate record produced by the GPU stages, in the reference's pre-sort order
- * (class order -> template_id -> ascending coarse cell; LL.cpp:1797-1939).  `work` is the index into
- * the matched-template sequence of this call; negative (-1 - index) when the candidate fell below
- * the threshold during refinement (LL.cpp:1935-1937).  16 bytes: the all-gather payload. */
+/* Pre-finish record of a candidate that survived refinement (LL.cpp:1855-1938), produced by the GPU
+ * stages.  `work` indexes the matched-template sequence of this call (global across shards); `seq` is
+ * the candidate's index in its shard's pre-sort order (template order, then ascending coarse cell;
+ * LL.cpp:1797-1939).  Records are appended unordered; sorting by (work, seq) restores the reference's
+ * pre-sort order.  16 bytes: the all-gather payload. */
 typedef struct lm_record {
-  int32_t x, y;
+  int16_t x, y;
   float similarity;
   int32_t work;
+  int32_t seq;
 } lm_record;
+
+/* A result block in device memory = this header followed by `capacity` lm_record slots. */
+typedef struct lm_result_header {
+  int32_t count;             /* records kept (may exceed capacity: only `capacity` were stored) */
+  int32_t coarse_candidates; /* candidates that passed the coarse threshold (LL.cpp:1836-1852) */
+  int32_t capacity;
+  int32_t shard;
+} lm_result_header;
 
 const char* lm_last_error(void);
 
@@ -93,17 +103,20 @@ int lm_run(lm_detector* d, float threshold);
 int lm_enqueue(lm_detector* d, float threshold);
 int lm_complete(lm_detector* d);
 
-/* Device-side results of the last lm_run: record array (lm_record[*], device pointer), device pointer
- * to the int32 record count, and capacity.  For fused/peer consumers (NCCL all-gather, ICP hand-off). */
-int lm_device_records(lm_detector* d, void** d_records, void** d_count, int64_t* capacity);
+/* Result block of the stages: by default an internal device buffer that grows on demand.  A caller
+ * that wants the block in its own device memory (e.g. the send buffer of an NCCL all-gather) sets it
+ * here; capacity is in records, the block is sizeof(lm_result_header) + capacity*sizeof(lm_record)
+ * bytes.  d_block = NULL returns to the internal buffer. */
+int lm_set_result_buffer(lm_detector* d, void* d_block, int64_t capacity_records);
+int lm_device_result(lm_detector* d, void** d_block, int64_t* capacity_records);
 
-/* Copy the records of the last lm_run to the host (count first, then exactly that many). */
+/* Copy the kept records of the last completed run to the host, sorted by (work, seq). */
 int lm_fetch_records(lm_detector* d, lm_record* out, int64_t cap, int64_t* n_out);
 
-/* Host finisher: drop below-threshold records, map work -> (class_index, template_id) for the current
+/* Host finisher: order records by (work, seq), map work -> (class_index, template_id) for the current
  * selection (work indices are global in the selected sequence), then the reference's
  * std::sort + std::unique (LL.cpp:1772-1774).  `records` may be the concatenation of all shards'
- * records in shard order. */
+ * records in any order. */
 int lm_finish(lm_detector* d, const lm_record* records, int64_t n, lm_match* out, int64_t cap, int64_t* n_out);
 
 /* Convenience = lm_upload_quantized + lm_run + lm_fetch_records + lm_finish (single GPU):
@@ -117,7 +130,7 @@ int lm_debug_linear_memories(lm_detector* d, int level, int modality, uint8_t* o
 /* Counters of the last lm_run: [0] templates scanned, [1] coarse candidates, [2] algorithmic bytes of
  * the coarse scan (sum over templates, modalities of features x positions),
  * [3] algorithmic bytes of the refinement (features x 256 per refined candidate and level),
- * [4] records kept after refinement. */
+ * [4] records kept after refinement.  [0],[2] describe this handle's shard. */
 int lm_counters(lm_detector* d, int64_t* out5);
 /* Per-stage device time in microseconds, from CUDA events recorded on the detector's stream around
  * each stage: [0] linear memories, [1] coarse scan, [2] candidate offsets, [3] refinement, [4] total.

@@ -30,6 +30,8 @@
 #include <emmintrin.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <chrono>
 #include <vector>
@@ -259,7 +261,7 @@ void patch8(const LinMem& lm, const Tmpl& t, uint8_t* dst /*256*/, int cx, int c
   }
 }
 
-struct Stats {
+struct alignas(64) Stats {  // one cache line per thread
   long coarse_byte_adds = 0, refine_byte_adds = 0, coarse_candidates = 0;
 };
 
@@ -422,8 +424,14 @@ long lmo_match(int L, int M, const int* T, const int* rows, const int* cols, con
     if (T[l] <= 0 || rows[l] % T[l] || cols[l] % T[l] || ((long)rows[l] * cols[l]) % 16) return -2;
   auto t0 = clk::now();
   std::vector<std::vector<LinMem>> pyr(L, std::vector<LinMem>(M));
-  for (int l = 0; l < L; ++l)
-    for (int m = 0; m < M; ++m) build_linmem(quantized[l * M + m], rows[l], cols[l], T[l], pyr[l][m]);
+  build_lut();
+  int used_threads = 1;
+#ifdef _OPENMP
+  if (n_threads > 1) used_threads = n_threads;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(used_threads) if (used_threads > 1)
+#endif
+  for (int lm = 0; lm < L * M; ++lm)
+    build_linmem(quantized[lm], rows[lm / M], cols[lm / M], T[lm / M], pyr[lm / M][lm % M]);
   auto t1 = clk::now();
 
   const int S = L * M;
@@ -432,10 +440,6 @@ long lmo_match(int L, int M, const int* T, const int* rows, const int* cols, con
   for (int c = 0; c < n_classes; ++c)
     for (int g = class_begin[c]; g < class_begin[c + 1]; ++g) class_of[g] = c;
 
-  int used_threads = 1;
-#ifdef _OPENMP
-  if (n_threads > 1) used_threads = n_threads;
-#endif
   std::vector<std::vector<Hit>> per(G);
   std::vector<Stats> stt(used_threads);
   int err = 0;
@@ -446,6 +450,7 @@ long lmo_match(int L, int M, const int* T, const int* rows, const int* cols, con
     int tid = 0;
 #ifdef _OPENMP
     tid = omp_get_thread_num();
+    if (g == 0 && getenv("LMO_DEBUG")) fprintf(stderr, "omp threads in region: %d\n", omp_get_num_threads());
 #endif
     std::vector<Tmpl> tp(S);
     for (int s = 0; s < S; ++s) {
@@ -455,7 +460,11 @@ long lmo_match(int L, int M, const int* T, const int* rows, const int* cols, con
       tp[s].nf = m4[3];
     }
     const int c = class_of[g];
-    int rc = match_template(pyr, T, L, M, tp.data(), threshold, c, g - class_begin[c], per[g], stt[tid]);
+    Stats local;
+    int rc = match_template(pyr, T, L, M, tp.data(), threshold, c, g - class_begin[c], per[g], local);
+    stt[tid].coarse_byte_adds += local.coarse_byte_adds;
+    stt[tid].refine_byte_adds += local.refine_byte_adds;
+    stt[tid].coarse_candidates += local.coarse_candidates;
     if (rc < 0) {
 #ifdef _OPENMP
 #pragma omp atomic write

@@ -9,6 +9,9 @@ import subprocess
 
 import numpy as np
 
+# libgomp's workers spin after a parallel region by default and starve the caller's serial code
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liblm_oracle.so")
 
