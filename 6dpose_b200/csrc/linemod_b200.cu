@@ -2,11 +2,7 @@
 //
 // Reference being replaced: linemodLevelup::Detector::match and everything below it
 // (linemodLevelup/linemodLevelup.cpp of meiqua/6DPose @ 619be57, "LL.cpp"):
-//   k_linear_memories  <- spread + computeResponseMaps + linearize      LL.cpp:1094-1243
-//   k_coarse_scan      <- similarity(_64) + addSimilarities(_64) + threshold loop
-//                                                                       LL.cpp:1284-1354, 1435-1534, 1836-1852
-//   k_scan_counts      <- candidates.push_back ordering (deterministic offsets)
-//   k_refine           <- similarityLocal(_64) + best-cell search + remove_if   LL.cpp:1366-1428, 1855-1938
+//   kernels (lm_kernels.cuh): k_linear_memories, k_coarse_bits / k_coarse_bytes, k_scan_counts, k_refine
 //   lm_finish (host)   <- std::sort + std::unique                       LL.cpp:1772-1774
 // Integer results (raw scores, x, y, template ids) are bit-exact; the float similarity is produced by
 // the same two IEEE operations as the reference ((raw * 100.f) / (4 * n)).
@@ -46,334 +42,14 @@ static int fail(int code, const char* fmt, ...) {
 
 extern "C" const char* lm_last_error(void) { return g_err; }
 
-// --------------------------------------------------------------------------------------------
-// device-side structures
-// --------------------------------------------------------------------------------------------
-#define LM_SKIP_BIT 0x80000000u  // in fxy: feature is outside the image at its own level (LL.cpp:1330)
-
-struct LevelDev {
-  const uint8_t* lm;  // [M][8][T*T][plane] response bytes, contiguous, zero pad after the end
-  int T, rows, cols, Wd, Hd, plane;
-  int off;              // T/2 + (T%2 - 1), LL.cpp:1846/1862
-  uint32_t mod_stride;  // 8*T*T*plane
-};
-
-// Per (template, slot): x = first feature, y = feature count, z = template_positions P at the
-// slot's level (LL.cpp:1309), w = width | height << 16.
-typedef int4 TSlot;
-
-__device__ __forceinline__ float lm_score(int raw, int nfeat) {
-  // (raw_score * 100.f) / (4 * num_features), LL.cpp:1842 / 1918 -- two correctly rounded float ops
-  return __fdiv_rn(__fmul_rn((float)raw, 100.f), (float)(4 * nfeat));
-}
-
-// response of orientation o against spread mask v: the active SIMILARITY_LUT (LL.cpp:1121) is
-// 4 if bit o is set, else 1 if a neighbouring orientation bit is set, else 0 (checked against the
-// table in tests).
-__device__ __forceinline__ uint32_t lm_response(uint32_t v, int o) {
-  uint32_t hit = (v >> o) & 1u;
-  uint32_t nb = ((v >> ((o + 1) & 7)) | (v >> ((o + 7) & 7))) & 1u;
-  return hit ? 4u : nb;
-}
-
-// --------------------------------------------------------------------------------------------
-// K1: spread (OR over the forward TxT window) -> response maps -> linear memories
-// --------------------------------------------------------------------------------------------
-struct LinMemParams {
-  const uint8_t* q[LM_MAX_MODALITIES];  // quantized u8 rows x cols
-  uint8_t* lm;
-  int T, rows, cols, Wd, Hd, plane;
-  uint32_t mod_stride;
-};
-
-__global__ void __launch_bounds__(256) k_linear_memories(LinMemParams p) {
-  const int m = blockIdx.y;
-  const int T2 = p.T * p.T;
-  const int n = T2 * p.plane;
-  const uint8_t* __restrict__ q = p.q[m];
-  uint8_t* __restrict__ out = p.lm + (size_t)m * p.mod_stride;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int g = i / p.plane, pos = i - g * p.plane;
-    const int gy = g / p.T, gx = g - gy * p.T;
-    const int py = pos / p.Wd, px = pos - py * p.Wd;
-    const int y = py * p.T + gy, x = px * p.T + gx;
-    const int y1 = min(y + p.T, p.rows), x1 = min(x + p.T, p.cols);
-    uint32_t v = 0;
-    for (int yy = y; yy < y1; ++yy) {
-      const uint8_t* row = q + (size_t)yy * p.cols;
-      for (int xx = x; xx < x1; ++xx) v |= __ldg(row + xx);
-    }
-#pragma unroll
-    for (int o = 0; o < 8; ++o) out[(size_t)o * n + i] = (uint8_t)lm_response(v, o);
-  }
-}
-
-// --------------------------------------------------------------------------------------------
-// K2: coarse similarity scan of one template per CTA over the lowest pyramid level
-// --------------------------------------------------------------------------------------------
-struct ScanParams {
-  LevelDev lv;
-  const TSlot* tslot;
-  const uint32_t* fbase;
-  const uint32_t* fxy;
-  const int32_t* work;  // template ids of this shard, in match order
-  int S, M, slot_low;
-  float threshold;
-  uint32_t* cand;  // [n_work][plane]: j | raw << 16, ascending j
-  int32_t* cnt;    // [n_work]
-};
-
-#define SCAN_FEAT_TILE 512
-
-__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* total) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  int inc = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += t;
-  }
-  __syncthreads();  // protect s_warp reuse
-  if (lane == 31) s_warp[wid] = inc;
-  __syncthreads();
-  if (wid == 0) {
-    int t = lane < nw ? s_warp[lane] : 0;
-    int ti = t;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int u = __shfl_up_sync(0xffffffffu, ti, d);
-      if (lane >= d) ti += u;
-    }
-    if (lane < nw) s_warp[lane] = ti - t;
-    if (lane == 31) s_warp[32] = ti;
-  }
-  __syncthreads();
-  *total = s_warp[32];
-  return s_warp[wid] + inc - v;
-}
-
-__global__ void __launch_bounds__(1024) k_coarse_scan(ScanParams p) {
-  __shared__ uint32_t s_base[SCAN_FEAT_TILE];
-  __shared__ int s_warp[33];
-  const int w = blockIdx.x;
-  const int g = p.work[w];
-  const int plane = p.lv.plane;
-  const uint32_t* __restrict__ lm32 = reinterpret_cast<const uint32_t*>(p.lv.lm);
-  uint32_t* __restrict__ cand = p.cand + (size_t)w * plane;
-
-  int nfeat = 0;
-  for (int m = 0; m < p.M; ++m) nfeat += p.tslot[(size_t)g * p.S + p.slot_low + m].y;
-
-  int emitted = 0;
-  for (int j0 = 0; j0 < plane; j0 += blockDim.x * 4) {
-    const int j = j0 + threadIdx.x * 4;
-    uint32_t s01 = 0, s23 = 0;  // u16 pairs: positions (j, j+1) and (j+2, j+3)
-    for (int m = 0; m < p.M; ++m) {
-      const TSlot ts = p.tslot[(size_t)g * p.S + p.slot_low + m];
-      const int P = ts.z;
-      // positions >= P stay zero ("dst zero elsewhere", LL.cpp:1314)
-      uint32_t pm = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) pm |= (j + k < P) ? (0xFFu << (8 * k)) : 0u;
-      for (int f0 = 0; f0 < ts.y; f0 += SCAN_FEAT_TILE) {
-        const int nt = min(SCAN_FEAT_TILE, ts.y - f0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < nt; i += blockDim.x) {
-          const uint32_t xy = p.fxy[ts.x + f0 + i];
-          s_base[i] = (xy & LM_SKIP_BIT) ? 0xFFFFFFFFu : p.fbase[ts.x + f0 + i];
-        }
-        __syncthreads();
-        if (pm) {
-          uint32_t a8 = 0;
-          int pend = 0;
-          for (int i = 0; i < nt; ++i) {
-            const uint32_t b = s_base[i];
-            if (b == 0xFFFFFFFFu) continue;
-            const uint32_t a = b + (uint32_t)j;
-            const uint32_t lo = __ldg(lm32 + (a >> 2));
-            const uint32_t hi = __ldg(lm32 + (a >> 2) + 1);
-            a8 += __funnelshift_r(lo, hi, (a & 3u) << 3) & pm;
-            if (++pend == 63) {  // 63 * 4 = 252 < 256: no carry between packed bytes
-              s01 += __byte_perm(a8, 0, 0x4140);
-              s23 += __byte_perm(a8, 0, 0x4342);
-              a8 = 0;
-              pend = 0;
-            }
-          }
-          s01 += __byte_perm(a8, 0, 0x4140);
-          s23 += __byte_perm(a8, 0, 0x4342);
-        }
-      }
-    }
-    // threshold (LL.cpp:1836-1852) + ordered emission
-    int raw[4] = {(int)(s01 & 0xFFFF), (int)(s01 >> 16), (int)(s23 & 0xFFFF), (int)(s23 >> 16)};
-    uint32_t pass = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (j + k < plane && lm_score(raw[k], nfeat) > p.threshold) pass |= 1u << k;
-    int total;
-    int rank = emitted + block_exclusive_scan(__popc(pass), s_warp, &total);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (pass & (1u << k)) cand[rank++] = (uint32_t)(j + k) | ((uint32_t)raw[k] << 16);
-    emitted += total;
-  }
-  if (threadIdx.x == 0) p.cnt[w] = emitted;
-}
-
-// --------------------------------------------------------------------------------------------
-// exclusive scan of the per-template candidate counts -> global candidate offsets (ordered)
-// --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
-                                                     lm_result_header* __restrict__ hdr, int capacity, int shard) {
-  __shared__ int s_warp[33];
-  const int per = (n + blockDim.x - 1) / blockDim.x;
-  const int b = threadIdx.x * per, e = min(b + per, n);
-  int sum = 0;
-  for (int i = b; i < e; ++i) sum += cnt[i];
-  int total;
-  int run = block_exclusive_scan(sum, s_warp, &total);
-  for (int i = b; i < e; ++i) {
-    off[i] = run;
-    run += cnt[i];
-  }
-  if (threadIdx.x == 0) {
-    off[n] = total;
-    hdr->count = 0;  // k_refine appends kept records behind the header
-    hdr->coarse_candidates = total;
-    hdr->capacity = capacity;
-    hdr->shard = shard;
-  }
-}
-
-// --------------------------------------------------------------------------------------------
-// K3: local refinement, one warp per coarse candidate, all upper pyramid levels
-// --------------------------------------------------------------------------------------------
-struct RefineParams {
-  LevelDev lv[LM_MAX_LEVELS];
-  const TSlot* tslot;
-  const uint32_t* fbase;
-  const uint32_t* fxy;
-  const int32_t* work;
-  const int32_t* off;   // [n_work + 1]
-  const uint32_t* cand;  // [n_work][plane_low]
-  int n_work, L, S, M;
-  int work_begin;  // global offset of this shard in the selected sequence
-  float threshold;
-  lm_result_header* hdr;  // result block: header, then `capacity` records
-  int32_t capacity;
-  unsigned long long* counters;  // [0] refinement feature-rows processed (x256 = bytes)
-};
-
-__global__ void __launch_bounds__(256) k_refine(RefineParams p) {
-  const int lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int total = p.off[p.n_work];
-  const LevelDev low = p.lv[p.L - 1];
-  const int row = lane >> 1, half = lane & 1;
-  unsigned long long feats_done = 0;
-  lm_record* __restrict__ out = reinterpret_cast<lm_record*>(p.hdr + 1);
-
-  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < total; c += nwarps) {
-    // template of candidate c: last w with off[w] <= c
-    int lo = 0, hi = p.n_work;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (p.off[mid] <= c) lo = mid; else hi = mid;
-    }
-    const int w = lo;
-    const int g = p.work[w];
-    const uint32_t cj = p.cand[(size_t)w * low.plane + (c - p.off[w])];
-    const int j = cj & 0xFFFF;
-    int nfeat = 0;
-    for (int m = 0; m < p.M; ++m) nfeat += p.tslot[(size_t)g * p.S + (p.L - 1) * p.M + m].y;
-    int x = (j % low.Wd) * low.T + low.off;
-    int y = (j / low.Wd) * low.T + low.off;
-    float sim = lm_score((int)(cj >> 16), nfeat);
-    bool kept = true;
-
-    for (int l = p.L - 2; l >= 0 && kept; --l) {
-      const LevelDev lv = p.lv[l];
-      const uint32_t* __restrict__ lm32 = reinterpret_cast<const uint32_t*>(lv.lm);
-      const TSlot t0 = p.tslot[(size_t)g * p.S + l * p.M];
-      const int T = lv.T, border = 8 * T;
-      const int max_x = lv.cols - (t0.w & 0xFFFF) - border;
-      const int max_y = lv.rows - (int)((unsigned)t0.w >> 16) - border;
-      x = x * 2 + 1;
-      y = y * 2 + 1;
-      x = max(x, border); y = max(y, border);  // LL.cpp:1875-1880 (max first, then min)
-      x = min(x, max_x);  y = min(y, max_y);
-      const int cx = x / T - 8, cy = y / T - 8;  // truncating division, LL.cpp:1380-1381
-      const int ox = cx * T, oy = cy * T;
-      const int shift = cy * lv.Wd + cx + row * lv.Wd + half * 8;
-
-      uint32_t s01 = 0, s23 = 0, s45 = 0, s67 = 0;
-      int nf2 = 0;
-      for (int m = 0; m < p.M; ++m) {
-        const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
-        nf2 += ts.y;
-        uint32_t a8 = 0, b8 = 0;
-        int pend = 0;
-        for (int i = 0; i < ts.y; ++i) {
-          const uint32_t xy = __ldg(p.fxy + ts.x + i);
-          const int fx = (int)(xy & 0x7FFFu) + ox, fy = (int)((xy >> 16) & 0x7FFFu) + oy;
-          if (fx < 0 || fy < 0 || fx >= lv.cols || fy >= lv.rows) continue;  // LL.cpp:1394
-          const uint32_t a = __ldg(p.fbase + ts.x + i) + (uint32_t)shift;
-          const uint32_t w0 = __ldg(lm32 + (a >> 2));
-          const uint32_t w1 = __ldg(lm32 + (a >> 2) + 1);
-          const uint32_t w2 = __ldg(lm32 + (a >> 2) + 2);
-          const uint32_t sh = (a & 3u) << 3;
-          a8 += __funnelshift_r(w0, w1, sh);
-          b8 += __funnelshift_r(w1, w2, sh);
-          ++feats_done;
-          if (++pend == 63) {
-            s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
-            s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
-            a8 = b8 = 0;
-            pend = 0;
-          }
-        }
-        s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
-        s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
-      }
-      // best cell: strict > in row-major order == max raw, lowest cell index (LL.cpp:1910-1927)
-      const uint32_t v[8] = {s01 & 0xFFFF, s01 >> 16, s23 & 0xFFFF, s23 >> 16,
-                             s45 & 0xFFFF, s45 >> 16, s67 & 0xFFFF, s67 >> 16};
-      uint32_t key = 0;
-      const int cell0 = row * 16 + half * 8;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) key = max(key, (v[k] << 8) | (uint32_t)(255 - (cell0 + k)));
-      key = __reduce_max_sync(0xffffffffu, key);
-      const int best_raw = (int)(key >> 8);
-      int br = -1, bc = -1;
-      if (best_raw > 0) {
-        const int cell = 255 - (int)(key & 255u);
-        br = cell >> 4;
-        bc = cell & 15;
-      }
-      sim = lm_score(best_raw, nf2);
-      x = (x / T - 8 + bc) * T + lv.off;  // LL.cpp:1930-1931
-      y = (y / T - 8 + br) * T + lv.off;
-      kept = !(sim < p.threshold);  // remove_if(similarity < threshold), LL.cpp:1935-1937
-    }
-    if (lane == 0 && kept) {
-      // unordered append; (work, seq) restores the reference's pre-sort order on the host
-      const int slot = atomicAdd(&p.hdr->count, 1);
-      if (slot < p.capacity) {
-        lm_record r;
-        r.x = (int16_t)x; r.y = (int16_t)y; r.similarity = sim;
-        r.work = p.work_begin + w;
-        r.seq = c;
-        out[slot] = r;
-      }
-    }
-  }
-  if (lane == 0 && feats_done) atomicAdd(p.counters + 0, feats_done);
-}
+#include "lm_kernels.cuh"
 
 // --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
+#define LM_MAX_ROUNDS 5
+#define LM_BITS_SMEM_LIMIT (200 * 1024)
+
 struct LevelHost {
   int T = 0, rows = 0, cols = 0, Wd = 0, Hd = 0, plane = 0;
   uint8_t* d_q[LM_MAX_MODALITIES] = {nullptr, nullptr};           // owned upload buffers
@@ -381,6 +57,8 @@ struct LevelHost {
   uint8_t* d_lm = nullptr;
   size_t lm_bytes = 0;
   uint32_t mod_stride = 0;
+  uint32_t* d_bp = nullptr;  // lowest level only: spread bit-planes [M][8][lbw]
+  int lbw = 0, nwords = 0, rounds = 0;
 };
 
 struct lm_detector {
@@ -399,6 +77,8 @@ struct lm_detector {
   TSlot* d_tslot = nullptr;
   uint32_t* d_fbase = nullptr;
   uint32_t* d_fxy = nullptr;
+  uint2* d_fdesc = nullptr;          // lowest-level features, bit-plane addressing
+  std::vector<uint8_t> bits_ok;      // per template: the bit-sliced coarse kernel may take it
   int prep_rows[LM_MAX_LEVELS] = {0}, prep_cols[LM_MAX_LEVELS] = {0};
   bool prepared = false;
   std::vector<TSlot> h_tslot;
@@ -409,10 +89,13 @@ struct lm_detector {
   int64_t shard_begin = 0, shard_count = 0;
   int shard_index = 0, shard_n = 1;
   int32_t* d_work = nullptr;
+  int32_t* d_items_bits = nullptr; int n_items_bits = 0;    // work items per coarse kernel
+  int32_t* d_items_bytes = nullptr; int n_items_bytes = 0;
   bool work_dirty = true;
 
   // per-run buffers
-  uint32_t* d_cand = nullptr; size_t cand_elems = 0;
+  uint32_t* d_mask = nullptr; size_t mask_elems = 0;  // [n_work][nwords] coarse pass bits
+  uint16_t* d_raw = nullptr; size_t raw_elems = 0;    // [n_work][plane] coarse raw scores (passing cells)
   int32_t* d_cnt = nullptr; int32_t* d_off = nullptr; size_t cnt_elems = 0;
   // result block (device): lm_result_header + capacity records; internal unless the caller set one
   lm_result_header* d_res = nullptr; int64_t res_cap = 0; bool res_external = false;
@@ -440,6 +123,8 @@ static void free_level(LevelHost& l) {
   }
   if (l.d_lm) cudaFree(l.d_lm);
   l.d_lm = nullptr;
+  if (l.d_bp) cudaFree(l.d_bp);
+  l.d_bp = nullptr;
 }
 
 extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** out) {
@@ -472,8 +157,9 @@ extern "C" void lm_destroy(lm_detector* d) {
   cudaSetDevice(d->device);
   if (d->stream) cudaStreamSynchronize(d->stream);
   for (int l = 0; l < LM_MAX_LEVELS; ++l) free_level(d->lv[l]);
-  cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_work);
-  cudaFree(d->d_cand); cudaFree(d->d_cnt); cudaFree(d->d_off);
+  cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_fdesc); cudaFree(d->d_work);
+  cudaFree(d->d_items_bits); cudaFree(d->d_items_bytes);
+  cudaFree(d->d_mask); cudaFree(d->d_raw); cudaFree(d->d_cnt); cudaFree(d->d_off);
   cudaFree(d->d_res_own); cudaFree(d->d_counters);
   cudaFreeHost(d->h_counters); cudaFreeHost(d->h_res);
   for (cudaEvent_t e : d->tev) cudaEventDestroy(e);
@@ -521,12 +207,13 @@ extern "C" int lm_load_bank(lm_detector* d, int n_classes, const int32_t* class_
   d->tmeta.assign(tmeta, tmeta + (size_t)G * n_slots * 4);
   d->feats.assign(feats, feats + (size_t)n_feats * 3);
   d->feat_slot.swap(slot_of);
-  cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy);
-  d->d_tslot = nullptr; d->d_fbase = nullptr; d->d_fxy = nullptr;
+  cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_fdesc);
+  d->d_tslot = nullptr; d->d_fbase = nullptr; d->d_fxy = nullptr; d->d_fdesc = nullptr;
   if (G > 0) CU(cudaMalloc(&d->d_tslot, sizeof(TSlot) * (size_t)G * n_slots));
   if (n_feats > 0) {
     CU(cudaMalloc(&d->d_fbase, sizeof(uint32_t) * (size_t)n_feats));
     CU(cudaMalloc(&d->d_fxy, sizeof(uint32_t) * (size_t)n_feats));
+    CU(cudaMalloc(&d->d_fdesc, sizeof(uint2) * (size_t)n_feats));
   }
   d->prepared = false;
   d->have_run = false;
@@ -603,6 +290,8 @@ static int prepare_bank(lm_detector* d) {
   if (same) return LM_OK;
   const size_t nf = d->feat_slot.size();
   std::vector<uint32_t> fbase(nf, 0), fxy(nf, 0);
+  std::vector<uint2> fdesc(nf, make_uint2(0u, LM_SKIP_BIT));
+  const int low_level = d->L - 1;
   for (size_t i = 0; i < nf; ++i) {
     const int s = d->feat_slot[i];
     if (s == 255) continue;  // feature not referenced by any template
@@ -616,6 +305,14 @@ static int prepare_bank(lm_detector* d) {
     uint32_t v = (uint32_t)x | ((uint32_t)y << 16);
     if (x >= lv.cols || y >= lv.rows) v |= LM_SKIP_BIT;  // LL.cpp:1330
     fxy[i] = v;
+    if (l == low_level && lv.d_bp) {
+      // flat bit address inside the label block: grid * plane + position (same order as the bytes)
+      const uint64_t inner = (uint64_t)((y % T) * T + (x % T)) * lv.plane + (uint64_t)(y / T) * lv.Wd + (x / T);
+      uint2 dsc;
+      dsc.x = (uint32_t)((uint64_t)(m * 8 + lab) * lv.lbw + (inner >> 5));
+      dsc.y = (uint32_t)(inner & 31) | ((uint32_t)lab << 8) | (v & LM_SKIP_BIT);
+      fdesc[i] = dsc;
+    }
   }
   d->h_tslot.resize((size_t)d->G * d->S);
   for (int g = 0; g < d->G; ++g)
@@ -630,9 +327,27 @@ static int prepare_bank(lm_detector* d) {
       t.w = (int)((uint32_t)m4[0] | ((uint32_t)m4[1] << 16));
       d->h_tslot[(size_t)g * d->S + s] = t;
     }
+  // the bit-sliced coarse kernel counts in 8 bits and masks once: it takes templates with at most 255
+  // lowest-level features in total and the same template_positions in every modality
+  d->bits_ok.assign((size_t)d->G, 0);
+  {
+    const LevelHost& lv = d->lv[low_level];
+    for (int g = 0; g < d->G && lv.d_bp; ++g) {
+      int total = 0;
+      bool same = true;
+      const TSlot& t0 = d->h_tslot[(size_t)g * d->S + low_level * d->M];
+      for (int m = 0; m < d->M; ++m) {
+        const TSlot& t = d->h_tslot[(size_t)g * d->S + low_level * d->M + m];
+        total += t.y;
+        same = same && t.z == t0.z;
+      }
+      d->bits_ok[g] = (total <= 255 && same) ? 1 : 0;
+    }
+  }
   if (nf) {
     CU(cudaMemcpyAsync(d->d_fbase, fbase.data(), nf * 4, cudaMemcpyHostToDevice, d->stream));
     CU(cudaMemcpyAsync(d->d_fxy, fxy.data(), nf * 4, cudaMemcpyHostToDevice, d->stream));
+    CU(cudaMemcpyAsync(d->d_fdesc, fdesc.data(), nf * sizeof(uint2), cudaMemcpyHostToDevice, d->stream));
   }
   if (d->G) CU(cudaMemcpyAsync(d->d_tslot, d->h_tslot.data(), sizeof(TSlot) * d->h_tslot.size(), cudaMemcpyHostToDevice, d->stream));
   CU(cudaStreamSynchronize(d->stream));  // host vectors go out of scope
@@ -651,6 +366,23 @@ static int prepare_work(lm_detector* d) {
   if (n > 0) {
     CU(cudaMalloc(&d->d_work, sizeof(int32_t) * (size_t)n));
     CU(cudaMemcpyAsync(d->d_work, d->sel.data() + d->shard_begin, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+  }
+  {
+    std::vector<int32_t> ib, iy;
+    for (int64_t i = 0; i < n; ++i) (d->bits_ok[d->sel[d->shard_begin + i]] ? ib : iy).push_back((int32_t)i);
+    cudaFree(d->d_items_bits); d->d_items_bits = nullptr;
+    cudaFree(d->d_items_bytes); d->d_items_bytes = nullptr;
+    d->n_items_bits = (int)ib.size();
+    d->n_items_bytes = (int)iy.size();
+    if (!ib.empty()) {
+      CU(cudaMalloc(&d->d_items_bits, sizeof(int32_t) * ib.size()));
+      CU(cudaMemcpyAsync(d->d_items_bits, ib.data(), sizeof(int32_t) * ib.size(), cudaMemcpyHostToDevice, d->stream));
+    }
+    if (!iy.empty()) {
+      CU(cudaMalloc(&d->d_items_bytes, sizeof(int32_t) * iy.size()));
+      CU(cudaMemcpyAsync(d->d_items_bytes, iy.data(), sizeof(int32_t) * iy.size(), cudaMemcpyHostToDevice, d->stream));
+    }
     CU(cudaStreamSynchronize(d->stream));
   }
   if ((size_t)n + 1 > d->cnt_elems) {
@@ -709,6 +441,17 @@ static int size_levels(lm_detector* d, const int* rows, const int* cols, bool ne
       lv.lm_bytes = per_mod * d->M + slack;
       CU(cudaMalloc(&lv.d_lm, lv.lm_bytes));
       CU(cudaMemsetAsync(lv.d_lm, 0, lv.lm_bytes, d->stream));
+      lv.nwords = (lv.plane + 31) / 32;
+      lv.rounds = (lv.nwords + 31) / 32;
+      if (l == d->L - 1 && lv.rounds <= LM_MAX_ROUNDS) {
+        // label block: T*T*plane bits, then slack for the reads of lanes beyond the last word
+        const size_t bits = (size_t)lv.T * lv.T * lv.plane;
+        lv.lbw = (int)(((bits + 31) / 32 + 32 * (size_t)lv.rounds + 4 + 3) & ~(size_t)3);
+        const size_t words = (size_t)d->M * 8 * lv.lbw;
+        CU(cudaMalloc(&lv.d_bp, words * 4));
+        CU(cudaMemsetAsync(lv.d_bp, 0, words * 4, d->stream));
+      }
+      d->prepared = false;  // feature addresses depend on the frame size
     }
     if (need_upload_buffers)
       for (int m = 0; m < d->M; ++m)
@@ -764,6 +507,22 @@ static LevelDev level_dev(const LevelHost& h) {
   return v;
 }
 
+template <int R>
+static cudaError_t launch_coarse_bits(const BitScanParams& bp, bool smem, size_t smem_bytes, int grid, cudaStream_t st) {
+  if (smem) {
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(k_coarse_bits<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_BITS_SMEM_LIMIT + 4096);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    k_coarse_bits<R, true><<<grid, 512, smem_bytes, st>>>(bp);
+  } else {
+    k_coarse_bits<R, false><<<grid, 512, 0, st>>>(bp);
+  }
+  return cudaGetLastError();
+}
+
 // Enqueue every GPU stage of one frame on the detector's stream; no host synchronisation.
 static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
   const int n_work = (int)d->shard_count;
@@ -782,22 +541,48 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       for (int m = 0; m < d->M; ++m) p.q[m] = lv.q_src[m];
       p.lm = lv.d_lm; p.T = lv.T; p.rows = lv.rows; p.cols = lv.cols; p.Wd = lv.Wd; p.Hd = lv.Hd; p.plane = lv.plane;
       p.mod_stride = lv.mod_stride;
+      p.bp = lv.d_bp; p.lbw = lv.lbw;
       const int n = lv.T * lv.T * lv.plane;
       dim3 grid((unsigned)std::min((n + 255) / 256, d->sm_count * 8), (unsigned)d->M);
       k_linear_memories<<<grid, 256, 0, st>>>(p);
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[1], st));
-    if (n_work > 0) {
-      ScanParams sp;
+    // K2
+    if (d->n_items_bits > 0) {
+      BitScanParams bp;
+      bp.bp = low.d_bp; bp.bp_words = (uint32_t)((size_t)d->M * 8 * low.lbw);
+      bp.lbw = low.lbw; bp.plane = low.plane; bp.nwords = low.nwords;
+      bp.tslot = d->d_tslot; bp.fdesc = d->d_fdesc; bp.work = d->d_work;
+      bp.items = d->d_items_bits; bp.n_items = d->n_items_bits;
+      bp.S = d->S; bp.M = d->M; bp.slot_low = (d->L - 1) * d->M;
+      bp.threshold = threshold;
+      bp.mask = d->d_mask; bp.raw = d->d_raw; bp.cnt = d->d_cnt;
+      const size_t smem_bytes = (size_t)bp.bp_words * 4;
+      const bool smem = smem_bytes <= LM_BITS_SMEM_LIMIT;
+      const int grid = std::min(d->sm_count, (d->n_items_bits + 15) / 16);
+      cudaError_t e = cudaSuccess;
+      switch (low.rounds) {
+        case 1: e = launch_coarse_bits<1>(bp, smem, smem_bytes, grid, st); break;
+        case 2: e = launch_coarse_bits<2>(bp, smem, smem_bytes, grid, st); break;
+        case 3: e = launch_coarse_bits<3>(bp, smem, smem_bytes, grid, st); break;
+        case 4: e = launch_coarse_bits<4>(bp, smem, smem_bytes, grid, st); break;
+        default: e = launch_coarse_bits<5>(bp, smem, smem_bytes, grid, st); break;
+      }
+      if (e != cudaSuccess) return fail(LM_E_CUDA, "k_coarse_bits launch failed: %s", cudaGetErrorString(e));
+      ++d->launches;
+    }
+    if (d->n_items_bytes > 0) {
+      ByteScanParams sp;
       sp.lv = level_dev(low);
       sp.tslot = d->d_tslot; sp.fbase = d->d_fbase; sp.fxy = d->d_fxy; sp.work = d->d_work;
-      sp.S = d->S; sp.M = d->M; sp.slot_low = (d->L - 1) * d->M;
+      sp.items = d->d_items_bytes;
+      sp.S = d->S; sp.M = d->M; sp.slot_low = (d->L - 1) * d->M; sp.nwords = low.nwords;
       sp.threshold = threshold;
-      sp.cand = d->d_cand; sp.cnt = d->d_cnt;
+      sp.mask = d->d_mask; sp.raw = d->d_raw; sp.cnt = d->d_cnt;
       int bs = ((low.plane + 3) / 4 + 31) / 32 * 32;
       bs = std::max(32, std::min(bs, 1024));
-      k_coarse_scan<<<n_work, bs, 0, st>>>(sp);
+      k_coarse_bytes<<<d->n_items_bytes, bs, 0, st>>>(sp);
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[2], st));
@@ -812,8 +597,8 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     RefineParams rp;
     for (int l = 0; l < d->L; ++l) rp.lv[l] = level_dev(d->lv[l]);
     rp.tslot = d->d_tslot; rp.fbase = d->d_fbase; rp.fxy = d->d_fxy; rp.work = d->d_work;
-    rp.off = d->d_off; rp.cand = d->d_cand;
-    rp.n_work = n_work; rp.L = d->L; rp.S = d->S; rp.M = d->M;
+    rp.off = d->d_off; rp.mask = d->d_mask; rp.raw = d->d_raw;
+    rp.n_work = n_work; rp.nwords = low.nwords; rp.L = d->L; rp.S = d->S; rp.M = d->M;
     rp.work_begin = (int)d->shard_begin;
     rp.threshold = threshold;
     rp.hdr = d->d_res; rp.capacity = (int32_t)d->res_cap;
@@ -841,12 +626,19 @@ static int enqueue_readback(lm_detector* d) {
 static int ensure_run_buffers(lm_detector* d) {
   const int64_t n_work = d->shard_count;
   const LevelHost& low = d->lv[d->L - 1];
-  const size_t need = (size_t)std::max<int64_t>(n_work, 1) * low.plane;
-  if (need > d->cand_elems) {
-    cudaFree(d->d_cand);
-    d->d_cand = nullptr;
-    d->cand_elems = need;
-    CU(cudaMalloc(&d->d_cand, sizeof(uint32_t) * need));
+  const size_t need_m = (size_t)std::max<int64_t>(n_work, 1) * low.nwords;
+  if (need_m > d->mask_elems) {
+    cudaFree(d->d_mask);
+    d->d_mask = nullptr;
+    d->mask_elems = need_m;
+    CU(cudaMalloc(&d->d_mask, sizeof(uint32_t) * need_m));
+  }
+  const size_t need_r = (size_t)std::max<int64_t>(n_work, 1) * low.plane;
+  if (need_r > d->raw_elems) {
+    cudaFree(d->d_raw);
+    d->d_raw = nullptr;
+    d->raw_elems = need_r;
+    CU(cudaMalloc(&d->d_raw, sizeof(uint16_t) * need_r));
   }
   if (!d->res_external) {
     if (d->res_cap_own == 0) {

@@ -1,0 +1,620 @@
+// lm_kernels.cuh -- device code of the LINEMOD match path (sm_100a).
+//
+// Reference functions replaced (linemodLevelup/linemodLevelup.cpp of meiqua/6DPose @ 619be57, "LL.cpp"):
+//   k_linear_memories  <- spread + computeResponseMaps + linearize          LL.cpp:1094-1243
+//   k_coarse_bits      <- similarity(_64) + addSimilarities(_64) + threshold loop (bit-sliced)
+//   k_coarse_bytes     <- the same, byte-wise (templates the bit-sliced kernel does not take)
+//                                                                           LL.cpp:1284-1354, 1435-1534, 1836-1852
+//   k_scan_counts      <- candidates.push_back ordering (deterministic offsets)
+//   k_refine           <- similarityLocal(_64) + best-cell search + remove_if   LL.cpp:1366-1428, 1855-1938
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "linemod_b200.h"
+
+#define LM_SKIP_BIT 0x80000000u  // feature lies outside the image at its own level (LL.cpp:1330)
+
+struct LevelDev {
+  const uint8_t* lm;  // [M][8][T*T][plane] response bytes, contiguous, zero pad after the end
+  int T, rows, cols, Wd, Hd, plane;
+  int off;              // T/2 + (T%2 - 1), LL.cpp:1846/1862
+  uint32_t mod_stride;  // 8*T*T*plane
+};
+
+// Per (template, slot): x = first feature, y = feature count, z = template_positions P at the
+// slot's level (LL.cpp:1309), w = width | height << 16.
+typedef int4 TSlot;
+
+__device__ __forceinline__ float lm_score(int raw, int nfeat) {
+  // (raw_score * 100.f) / (4 * num_features), LL.cpp:1842 / 1918 -- two correctly rounded float ops
+  return __fdiv_rn(__fmul_rn((float)raw, 100.f), (float)(4 * nfeat));
+}
+
+// Smallest raw score whose similarity exceeds the threshold (the float compare of LL.cpp:1842-1844
+// is monotone in raw).  Returns 4*nfeat + 1 when nothing can pass.
+__device__ __forceinline__ int lm_min_passing_raw(float threshold, int nfeat) {
+  int lo = 0, hi = 4 * nfeat + 1;  // invariant: everything >= hi passes (hi = max+1 is "nothing")
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (lm_score(mid, nfeat) > threshold) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// response of orientation o against spread mask v: the active SIMILARITY_LUT (LL.cpp:1121) is
+// 4 if bit o is set, else 1 if a neighbouring orientation bit is set, else 0 (checked against the
+// table in tests/test_oracle_cpu.py).
+__device__ __forceinline__ uint32_t lm_response(uint32_t v, int o) {
+  const uint32_t hit = (v >> o) & 1u;
+  const uint32_t nb = ((v >> ((o + 1) & 7)) | (v >> ((o + 7) & 7))) & 1u;
+  return hit ? 4u : nb;
+}
+
+// --------------------------------------------------------------------------------------------
+// K1: spread (OR over the forward TxT window) -> response maps -> linear memories
+//     (+ for the lowest level: the same spread masks as bit-planes, one bit per position and label)
+// --------------------------------------------------------------------------------------------
+struct LinMemParams {
+  const uint8_t* q[LM_MAX_MODALITIES];  // quantized u8 rows x cols
+  uint8_t* lm;
+  uint32_t* bp;  // optional: [M][8][lbw] words, bit (grid*plane + pos) of block (m, o) = spread bit o
+  int lbw;
+  int T, rows, cols, Wd, Hd, plane;
+  uint32_t mod_stride;
+};
+
+__global__ void __launch_bounds__(256) k_linear_memories(LinMemParams p) {
+  const int m = blockIdx.y;
+  const int n = p.T * p.T * p.plane;
+  const uint8_t* __restrict__ q = (m == 0) ? p.q[0] : p.q[1];
+  uint8_t* __restrict__ out = p.lm + (size_t)m * p.mod_stride;
+  const int n_up = (n + 255) & ~255;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_up; i += gridDim.x * blockDim.x) {
+    uint32_t v = 0;
+    if (i < n) {
+      const int g = i / p.plane, pos = i - g * p.plane;
+      const int gy = g / p.T, gx = g - gy * p.T;
+      const int py = pos / p.Wd, px = pos - py * p.Wd;
+      const int y = py * p.T + gy, x = px * p.T + gx;
+      const int y1 = min(y + p.T, p.rows), x1 = min(x + p.T, p.cols);
+      for (int yy = y; yy < y1; ++yy) {
+        const uint8_t* row = q + (size_t)yy * p.cols;
+        for (int xx = x; xx < x1; ++xx) v |= __ldg(row + xx);
+      }
+#pragma unroll
+      for (int o = 0; o < 8; ++o) out[(size_t)o * n + i] = (uint8_t)lm_response(v, o);
+    }
+    if (p.bp) {  // warp-uniform; i is 32-aligned across the warp
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const uint32_t b = __ballot_sync(0xffffffffu, (v >> o) & 1u);
+        if ((threadIdx.x & 31) == 0 && i < n) p.bp[(size_t)(m * 8 + o) * p.lbw + (i >> 5)] = b;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// warp / block helpers
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  __syncthreads();  // protect s_warp reuse
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int t = lane < nw ? s_warp[lane] : 0;
+    int ti = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, ti, d);
+      if (lane >= d) ti += u;
+    }
+    if (lane < nw) s_warp[lane] = ti - t;
+    if (lane == 31) s_warp[32] = ti;
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[wid] + inc - v;
+}
+
+// --------------------------------------------------------------------------------------------
+// K2 (bit-sliced): coarse similarity scan over the lowest pyramid level.
+//
+// The response of a feature with orientation o at a position is 4*H + N with H = spread bit o and
+// N = (spread bit o-1 | spread bit o+1) & ~H.  The spread bits are kept as bit-planes over the
+// linear-memory positions (same flat order as the byte linear memories, so reads that run past a
+// grid row continue into the next one exactly as the reference's do).  One warp owns one template:
+// lane i holds positions 32*(i + 32 r) ... +31 of round r, and adds the H and N planes of every
+// feature into two vertical (bit-sliced) counters with carry-save adders; the score 4*CH + CN, the
+// threshold compare and the candidate mask are evaluated bit-sliced as well.  All bit-planes of the
+// level (153.6 KB at 640x480) sit in shared memory, staged by one bulk (TMA) copy per CTA.
+// --------------------------------------------------------------------------------------------
+struct BitScanParams {
+  const uint32_t* bp;   // [M*8][lbw]
+  uint32_t bp_words;    // M*8*lbw
+  int lbw, plane, nwords;
+  const TSlot* tslot;
+  const uint2* fdesc;   // per feature: x = word of the H_o window start inside bp, y = shift | o << 8 | skip << 31
+  const int32_t* work;  // template id per work item
+  const int32_t* items; // work items taken by this kernel
+  int n_items;
+  int S, M, slot_low;
+  float threshold;
+  uint32_t* mask;  // [n_work][nwords] pass bits, position order
+  uint16_t* raw;   // [n_work][plane] raw score, written at passing positions only
+  int32_t* cnt;    // [n_work]
+};
+
+#define CSA(sum, carry, a, b, c)                 \
+  {                                              \
+    const uint32_t a_ = (a), b_ = (b), c_ = (c); \
+    carry = (a_ & b_) | (c_ & (a_ ^ b_));        \
+    sum = a_ ^ b_ ^ c_;                          \
+  }
+
+// add eight 1-bit planes x[0..7] into the 8-bit vertical counter c[0..7]
+__device__ __forceinline__ void vc_add8(uint32_t (&c)[8], const uint32_t (&x)[8]) {
+  uint32_t t1a, t1b, t1c, t1d, t2a, t2b, t3;
+  CSA(c[0], t1a, c[0], x[0], x[1]);
+  CSA(c[0], t1b, c[0], x[2], x[3]);
+  CSA(c[1], t2a, c[1], t1a, t1b);
+  CSA(c[0], t1c, c[0], x[4], x[5]);
+  CSA(c[0], t1d, c[0], x[6], x[7]);
+  CSA(c[1], t2b, c[1], t1c, t1d);
+  CSA(c[2], t3, c[2], t2a, t2b);
+#pragma unroll
+  for (int b = 3; b < 8; ++b) {  // ripple the weight-8 carry
+    const uint32_t k = c[b] & t3;
+    c[b] ^= t3;
+    t3 = k;
+  }
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int R, bool kSmem>
+__global__ void __launch_bounds__(512, 1) k_coarse_bits(BitScanParams p) {
+  extern __shared__ __align__(128) uint32_t s_bp[];
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_next;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // this CTA's slice of the work items; warps pull from it dynamically
+  const int t0 = (int)(((long long)p.n_items * blockIdx.x) / gridDim.x);
+  const int t1 = (int)(((long long)p.n_items * (blockIdx.x + 1)) / gridDim.x);
+  if (threadIdx.x == 0) s_next = t0 + nwarps;
+
+  const uint32_t* __restrict__ bp = p.bp;
+  if (kSmem) {
+    // one elected thread stages every bit-plane with bulk async copies (TMA, 1-D) onto an mbarrier
+    const uint32_t bar = smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = p.bp_words * 4u;  // multiple of 16 (lbw is a multiple of 4)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      const char* src = reinterpret_cast<const char*>(p.bp);
+      uint32_t dst = smem_u32(s_bp);
+      for (uint32_t done = 0; done < bytes;) {
+        const uint32_t n = min(bytes - done, 32768u);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + done),
+                     "l"(src + done), "r"(n), "r"(bar)
+                     : "memory");
+        done += n;
+      }
+    }
+    // everyone waits for phase 0 of the barrier
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar)
+        : "memory");
+    bp = s_bp;
+  } else {
+    __syncthreads();
+  }
+
+  int it = t0 + warp;
+  while (it < t1) {
+    const int w = p.items[it];
+    const int g = p.work[w];
+    int nfeat = 0;
+    for (int m = 0; m < p.M; ++m) nfeat += p.tslot[(size_t)g * p.S + p.slot_low + m].y;
+    const int P = p.tslot[(size_t)g * p.S + p.slot_low].z;  // equal for all modalities (host checked)
+
+    uint32_t ch[R][8], cn[R][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) ch[r][b] = cn[r][b] = 0u;
+
+    for (int m = 0; m < p.M; ++m) {
+      const TSlot ts = p.tslot[(size_t)g * p.S + p.slot_low + m];
+      const uint2* __restrict__ fd = p.fdesc + ts.x;
+      for (int f0 = 0; f0 < ts.y; f0 += 8) {
+        uint32_t xh[R][8], xn[R][8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          uint2 d = make_uint2(0u, LM_SKIP_BIT);
+          if (f0 + u < ts.y) d = __ldg(fd + f0 + u);
+          if (d.y & LM_SKIP_BIT) {  // warp-uniform
+#pragma unroll
+            for (int r = 0; r < R; ++r) xh[r][u] = xn[r][u] = 0u;
+          } else {
+            const int o = (d.y >> 8) & 7;
+            const uint32_t s = d.y & 31u;
+            const uint32_t* __restrict__ ph = bp + d.x + lane;
+            const uint32_t* __restrict__ pm = ph + (((o + 7) & 7) - o) * p.lbw;
+            const uint32_t* __restrict__ pp = ph + (((o + 1) & 7) - o) * p.lbw;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const uint32_t h = __funnelshift_r(ph[32 * r], ph[32 * r + 1], s);
+              const uint32_t a = __funnelshift_r(pm[32 * r], pm[32 * r + 1], s);
+              const uint32_t b = __funnelshift_r(pp[32 * r], pp[32 * r + 1], s);
+              xh[r][u] = h;
+              xn[r][u] = (a | b) & ~h;
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          vc_add8(ch[r], xh[r]);
+          vc_add8(cn[r], xn[r]);
+        }
+      }
+    }
+
+    // score = 4*CH + CN (bit-sliced ripple add), positions >= P are zero (LL.cpp:1314), compare with
+    // the smallest passing raw score, emit the pass mask and the raw scores of the passing positions
+    const int raw_min = lm_min_passing_raw(p.threshold, nfeat);
+    int my_count = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int idx = lane + 32 * r;
+      if (idx < p.nwords) {
+        const int j0 = idx * 32;
+        uint32_t live = 0xffffffffu;   // positions < P carry a score
+        uint32_t valid = 0xffffffffu;  // positions < plane exist
+        if (P - j0 < 32) live = (P - j0 <= 0) ? 0u : (0xffffffffu >> (32 - (P - j0)));
+        if (p.plane - j0 < 32) valid = 0xffffffffu >> (32 - (p.plane - j0));
+        uint32_t s[11];
+        s[0] = cn[r][0] & live;
+        s[1] = cn[r][1] & live;
+        uint32_t carry = 0u;
+#pragma unroll
+        for (int b = 2; b < 10; ++b) {
+          const uint32_t a = (b < 8) ? cn[r][b] : 0u;
+          const uint32_t h = ch[r][b - 2];
+          s[b] = (a ^ h ^ carry) & live;
+          carry = (a & h) | (carry & (a ^ h));
+        }
+        s[10] = carry & live;
+        uint32_t pass;
+        if (raw_min > 2047) {
+          pass = 0u;
+        } else {
+          uint32_t gt = 0u, eq = 0xffffffffu;
+#pragma unroll
+          for (int b = 10; b >= 0; --b) {
+            if ((raw_min >> b) & 1) {
+              eq &= s[b];
+            } else {
+              gt |= eq & s[b];
+              eq &= ~s[b];
+            }
+          }
+          pass = (gt | eq) & valid;
+        }
+        p.mask[(size_t)w * p.nwords + idx] = pass;
+        my_count += __popc(pass);
+        while (pass) {
+          const int b = __ffs(pass) - 1;
+          pass &= pass - 1;
+          uint32_t v = 0;
+#pragma unroll
+          for (int k = 0; k < 11; ++k) v |= ((s[k] >> b) & 1u) << k;
+          p.raw[(size_t)w * p.plane + j0 + b] = (uint16_t)v;
+        }
+      }
+    }
+    my_count = __reduce_add_sync(0xffffffffu, my_count);
+    if (lane == 0) p.cnt[w] = my_count;
+
+    int nxt = 0;
+    if (lane == 0) nxt = atomicAdd(&s_next, 1);
+    it = __shfl_sync(0xffffffffu, nxt, 0);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// K2 (byte-wise): same result for templates the bit-sliced kernel does not take (more than 255
+// features in total, modalities with different template_positions, very large frames).  One CTA per
+// template, packed-byte accumulation of the response bytes straight from the linear memories.
+// --------------------------------------------------------------------------------------------
+struct ByteScanParams {
+  LevelDev lv;
+  const TSlot* tslot;
+  const uint32_t* fbase;
+  const uint32_t* fxy;
+  const int32_t* work;
+  const int32_t* items;
+  int S, M, slot_low, nwords;
+  float threshold;
+  uint32_t* mask;
+  uint16_t* raw;
+  int32_t* cnt;
+};
+
+#define SCAN_FEAT_TILE 512
+
+__global__ void __launch_bounds__(1024) k_coarse_bytes(ByteScanParams p) {
+  __shared__ uint32_t s_base[SCAN_FEAT_TILE];
+  __shared__ int s_count;
+  const int w = p.items[blockIdx.x];
+  const int g = p.work[w];
+  const int plane = p.lv.plane;
+  const int lane = threadIdx.x & 31;
+  const uint32_t* __restrict__ lm32 = reinterpret_cast<const uint32_t*>(p.lv.lm);
+  if (threadIdx.x == 0) s_count = 0;
+
+  int nfeat = 0;
+  for (int m = 0; m < p.M; ++m) nfeat += p.tslot[(size_t)g * p.S + p.slot_low + m].y;
+
+  int counted = 0;
+  // every thread owns 4 consecutive positions; a warp therefore owns 4 mask words per pass
+  const int span = blockDim.x * 4;
+  const int plane_up = (plane + 127) & ~127;
+  for (int j0 = 0; j0 < plane_up; j0 += span) {
+    const int j = j0 + threadIdx.x * 4;
+    uint32_t s01 = 0, s23 = 0;  // u16 pairs: positions (j, j+1) and (j+2, j+3)
+    for (int m = 0; m < p.M; ++m) {
+      const TSlot ts = p.tslot[(size_t)g * p.S + p.slot_low + m];
+      const int P = ts.z;
+      uint32_t pm = 0;  // positions >= P stay zero ("dst zero elsewhere", LL.cpp:1314)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pm |= (j + k < P) ? (0xFFu << (8 * k)) : 0u;
+      for (int f0 = 0; f0 < ts.y; f0 += SCAN_FEAT_TILE) {
+        const int nt = min(SCAN_FEAT_TILE, ts.y - f0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+          const uint32_t xy = p.fxy[ts.x + f0 + i];
+          s_base[i] = (xy & LM_SKIP_BIT) ? 0xFFFFFFFFu : p.fbase[ts.x + f0 + i];
+        }
+        __syncthreads();
+        if (pm) {
+          uint32_t a8 = 0;
+          int pend = 0;
+          for (int i = 0; i < nt; ++i) {
+            const uint32_t b = s_base[i];
+            if (b == 0xFFFFFFFFu) continue;
+            const uint32_t a = b + (uint32_t)j;
+            const uint32_t lo = __ldg(lm32 + (a >> 2));
+            const uint32_t hi = __ldg(lm32 + (a >> 2) + 1);
+            a8 += __funnelshift_r(lo, hi, (a & 3u) << 3) & pm;
+            if (++pend == 63) {  // 63 * 4 = 252 < 256: no carry between packed bytes
+              s01 += __byte_perm(a8, 0, 0x4140);
+              s23 += __byte_perm(a8, 0, 0x4342);
+              a8 = 0;
+              pend = 0;
+            }
+          }
+          s01 += __byte_perm(a8, 0, 0x4140);
+          s23 += __byte_perm(a8, 0, 0x4342);
+        }
+      }
+    }
+    // threshold (LL.cpp:1836-1852)
+    const int raw[4] = {(int)(s01 & 0xFFFF), (int)(s01 >> 16), (int)(s23 & 0xFFFF), (int)(s23 >> 16)};
+    uint32_t pass = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (j + k < plane && lm_score(raw[k], nfeat) > p.threshold) {
+        pass |= 1u << k;
+        p.raw[(size_t)w * plane + j + k] = (uint16_t)raw[k];
+      }
+    // 8 lanes -> one 32-bit mask word
+    uint32_t word = pass << (4 * (lane & 7));
+    word |= __shfl_xor_sync(0xffffffffu, word, 1);
+    word |= __shfl_xor_sync(0xffffffffu, word, 2);
+    word |= __shfl_xor_sync(0xffffffffu, word, 4);
+    if ((lane & 7) == 0 && (j >> 5) < p.nwords) p.mask[(size_t)w * p.nwords + (j >> 5)] = word;
+    counted += __popc(pass);
+  }
+  counted = __reduce_add_sync(0xffffffffu, counted);
+  __syncthreads();
+  if (lane == 0 && counted) atomicAdd(&s_count, counted);
+  __syncthreads();
+  if (threadIdx.x == 0) p.cnt[w] = s_count;
+}
+
+// --------------------------------------------------------------------------------------------
+// exclusive scan of the per-template candidate counts -> global candidate offsets (ordered)
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
+                                                     lm_result_header* __restrict__ hdr, int capacity, int shard) {
+  __shared__ int s_warp[33];
+  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int b = threadIdx.x * per, e = min(b + per, n);
+  int sum = 0;
+  for (int i = b; i < e; ++i) sum += cnt[i];
+  int total;
+  int run = block_exclusive_scan(sum, s_warp, &total);
+  for (int i = b; i < e; ++i) {
+    off[i] = run;
+    run += cnt[i];
+  }
+  if (threadIdx.x == 0) {
+    off[n] = total;
+    hdr->count = 0;  // k_refine appends kept records behind the header
+    hdr->coarse_candidates = total;
+    hdr->capacity = capacity;
+    hdr->shard = shard;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// K3: local refinement, one warp per coarse candidate, all upper pyramid levels
+// --------------------------------------------------------------------------------------------
+struct RefineParams {
+  LevelDev lv[LM_MAX_LEVELS];
+  const TSlot* tslot;
+  const uint32_t* fbase;
+  const uint32_t* fxy;
+  const int32_t* work;
+  const int32_t* off;    // [n_work + 1]
+  const uint32_t* mask;  // [n_work][nwords]
+  const uint16_t* raw;   // [n_work][plane_low]
+  int n_work, nwords, L, S, M;
+  int work_begin;  // global offset of this shard in the selected sequence
+  float threshold;
+  lm_result_header* hdr;  // result block: header, then `capacity` records
+  int32_t capacity;
+  unsigned long long* counters;  // [0] refinement feature-rows processed (x256 = bytes)
+};
+
+__global__ void __launch_bounds__(256) k_refine(RefineParams p) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int total = p.off[p.n_work];
+  const LevelDev low = p.lv[p.L - 1];
+  const int row = lane >> 1, half = lane & 1;
+  unsigned long long feats_done = 0;
+  lm_record* __restrict__ out = reinterpret_cast<lm_record*>(p.hdr + 1);
+
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < total; c += nwarps) {
+    // template of candidate c: last w with off[w] <= c
+    int lo = 0, hi = p.n_work;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (p.off[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int w = lo;
+    const int g = p.work[w];
+    // the (c - off[w])-th set bit of the template's pass mask, in position order
+    int j;
+    {
+      int k = c - p.off[w];
+      const uint32_t* __restrict__ mk = p.mask + (size_t)w * p.nwords;
+      j = 0;
+      for (int base = 0; base < p.nwords; base += 32) {
+        const uint32_t word = (base + lane < p.nwords) ? mk[base + lane] : 0u;
+        const int pc = __popc(word);
+        int inc = pc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += t;
+        }
+        const int tot = __shfl_sync(0xffffffffu, inc, 31);
+        if (k < tot) {
+          const uint32_t hit = __ballot_sync(0xffffffffu, k < inc);
+          const int src = __ffs(hit) - 1;  // first lane whose inclusive prefix exceeds k
+          const int before = __shfl_sync(0xffffffffu, inc - pc, src);
+          const uint32_t wsel = __shfl_sync(0xffffffffu, word, src);
+          j = (base + src) * 32 + (int)__fns(wsel, 0, k - before + 1);
+          break;
+        }
+        k -= tot;
+      }
+    }
+    int nfeat = 0;
+    for (int m = 0; m < p.M; ++m) nfeat += p.tslot[(size_t)g * p.S + (p.L - 1) * p.M + m].y;
+    int x = (j % low.Wd) * low.T + low.off;
+    int y = (j / low.Wd) * low.T + low.off;
+    float sim = lm_score((int)p.raw[(size_t)w * low.plane + j], nfeat);
+    bool kept = true;
+
+    for (int l = p.L - 2; l >= 0 && kept; --l) {
+      const LevelDev lv = p.lv[l];
+      const uint32_t* __restrict__ lm32 = reinterpret_cast<const uint32_t*>(lv.lm);
+      const TSlot t0 = p.tslot[(size_t)g * p.S + l * p.M];
+      const int T = lv.T, border = 8 * T;
+      const int max_x = lv.cols - (t0.w & 0xFFFF) - border;
+      const int max_y = lv.rows - (int)((unsigned)t0.w >> 16) - border;
+      x = x * 2 + 1;
+      y = y * 2 + 1;
+      x = max(x, border); y = max(y, border);  // LL.cpp:1875-1880 (max first, then min)
+      x = min(x, max_x);  y = min(y, max_y);
+      const int cx = x / T - 8, cy = y / T - 8;  // truncating division, LL.cpp:1380-1381
+      const int ox = cx * T, oy = cy * T;
+      const int shift = cy * lv.Wd + cx + row * lv.Wd + half * 8;
+
+      uint32_t s01 = 0, s23 = 0, s45 = 0, s67 = 0;
+      int nf2 = 0;
+      for (int m = 0; m < p.M; ++m) {
+        const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
+        nf2 += ts.y;
+        uint32_t a8 = 0, b8 = 0;
+        int pend = 0;
+        for (int i = 0; i < ts.y; ++i) {
+          const uint32_t xy = __ldg(p.fxy + ts.x + i);
+          const int fx = (int)(xy & 0x7FFFu) + ox, fy = (int)((xy >> 16) & 0x7FFFu) + oy;
+          if (fx < 0 || fy < 0 || fx >= lv.cols || fy >= lv.rows) continue;  // LL.cpp:1394
+          const uint32_t a = __ldg(p.fbase + ts.x + i) + (uint32_t)shift;
+          const uint32_t w0 = __ldg(lm32 + (a >> 2));
+          const uint32_t w1 = __ldg(lm32 + (a >> 2) + 1);
+          const uint32_t w2 = __ldg(lm32 + (a >> 2) + 2);
+          const uint32_t sh = (a & 3u) << 3;
+          a8 += __funnelshift_r(w0, w1, sh);
+          b8 += __funnelshift_r(w1, w2, sh);
+          ++feats_done;
+          if (++pend == 63) {
+            s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
+            s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
+            a8 = b8 = 0;
+            pend = 0;
+          }
+        }
+        s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
+        s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
+      }
+      // best cell: strict > in row-major order == max raw, lowest cell index (LL.cpp:1910-1927)
+      const uint32_t v[8] = {s01 & 0xFFFF, s01 >> 16, s23 & 0xFFFF, s23 >> 16,
+                             s45 & 0xFFFF, s45 >> 16, s67 & 0xFFFF, s67 >> 16};
+      uint32_t key = 0;
+      const int cell0 = row * 16 + half * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) key = max(key, (v[k] << 8) | (uint32_t)(255 - (cell0 + k)));
+      key = __reduce_max_sync(0xffffffffu, key);
+      const int best_raw = (int)(key >> 8);
+      int br = -1, bc = -1;
+      if (best_raw > 0) {
+        const int cell = 255 - (int)(key & 255u);
+        br = cell >> 4;
+        bc = cell & 15;
+      }
+      sim = lm_score(best_raw, nf2);
+      x = (x / T - 8 + bc) * T + lv.off;  // LL.cpp:1930-1931
+      y = (y / T - 8 + br) * T + lv.off;
+      kept = !(sim < p.threshold);  // remove_if(similarity < threshold), LL.cpp:1935-1937
+    }
+    if (lane == 0 && kept) {
+      // unordered append; (work, seq) restores the reference's pre-sort order on the host
+      const int slot = atomicAdd(&p.hdr->count, 1);
+      if (slot < p.capacity) {
+        lm_record r;
+        r.x = (int16_t)x; r.y = (int16_t)y; r.similarity = sim;
+        r.work = p.work_begin + w;
+        r.seq = c;
+        out[slot] = r;
+      }
+    }
+  }
+  if (lane == 0 && feats_done) atomicAdd(p.counters + 0, feats_done);
+}

@@ -49,6 +49,10 @@ def test_linear_memories_bit_exact(synth, oracle, T, W, H, nf):
     ([4, 8], 320, 256, 40, 35, 60.0),
     ([8], 320, 240, 40, 35, 60.0),       # single level: no refinement
     ([2, 4, 8], 640, 512, 96, 35, 70.0), # three levels
+    ([4, 8], 640, 480, 300, 35, 75.0),   # 300 features at the lowest level: byte-wise coarse kernel
+    ([4, 8], 800, 480, 150, 35, 75.0),   # 47 position words, bit-planes still fit shared memory
+    ([4, 8], 960, 640, 150, 35, 75.0),   # 75 position words (3 rounds), bit-planes read from global memory
+    ([4, 8], 1280, 960, 150, 20, 80.0),  # BASELINE config 5 frame size: 150 words (5 rounds)
 ])
 def test_match_bit_exact_synthetic(synth, oracle, T, W, H, nf, n, thr):
     bank = synth.synth_bank(n, num_features=nf, levels=len(T), seed=21, class_ids=("01_template", "02_template"))
@@ -63,3 +67,58 @@ def test_match_bit_exact_synthetic(synth, oracle, T, W, H, nf, n, thr):
     assert c["coarse_candidates"] == int(st["coarse_candidates"])
     assert c["scan_bytes"] == int(st["coarse_byte_adds"])
     assert c["refine_bytes"] == int(st["refine_byte_adds"])
+
+
+def test_match_mixed_kernels_and_ragged_templates(synth, oracle):
+    """Templates whose modalities have different sizes / feature counts (never produced by
+    cropTemplates, but legal input): unequal template_positions per modality, empty modality,
+    a template larger than the frame, out-of-image features.  Exercises the byte-wise coarse kernel
+    next to the bit-sliced one in the same call."""
+    T = [4, 8]
+    bank = synth.synth_bank(24, num_features=150, levels=2, seed=77)
+    tps = bank.classes["01_template"]
+    tps[1][3].width += 16            # L1 depth template wider than L1 colour template -> different P
+    tps[2][3].features = tps[2][3].features[:0]   # empty L1 depth modality
+    tps[3][2].width = 400; tps[3][2].height = 300; tps[3][3].width = 400; tps[3][3].height = 300  # P <= 0
+    tps[4][2].features[0, 0] = 330   # x beyond the 320-wide L1 image: skipped (LL.cpp:1330)
+    tps[5][0].features[3, 1] = 479   # L0 feature pushed out of the image by the patch offset
+    q, _ = synth.synth_frame(640, 480, levels=2, seed=4, bank=bank, plant=5, T=T)
+    nat, packed = _native(T, bank)
+    for thr in (60.0, 75.0):
+        got = nat.match_quantized(q, thr)
+        want, st = oracle.match(q, T, packed, thr, want_stats=True)
+        _assert_same(got, want)
+        c = nat.counters()
+        assert c["coarse_candidates"] == int(st["coarse_candidates"])
+        assert c["scan_bytes"] == int(st["coarse_byte_adds"])
+        assert c["refine_bytes"] == int(st["refine_byte_adds"])
+
+
+def test_negative_threshold_passes_every_cell(synth, oracle):
+    """threshold < 0: every sampled cell is a candidate, including the wrapped / zero ones beyond
+    template_positions (LL.cpp:1836-1852 scans all Hd x Wd cells)."""
+    T = [4, 8]
+    bank = synth.synth_bank(3, num_features=32, levels=2, seed=5)
+    q, _ = synth.synth_frame(320, 256, levels=2, seed=6, bank=bank, plant=1, T=T)
+    nat, packed = _native(T, bank)
+    got = nat.match_quantized(q, -1.0)
+    want, st = oracle.match(q, T, packed, -1.0, want_stats=True)
+    assert int(st["coarse_candidates"]) == 3 * (320 // 2 // 8) * (256 // 2 // 8)
+    _assert_same(got, want)
+
+
+def test_reference_assertion_is_an_error(synth, oracle):
+    """First modality < 64 features but a later one > 63: the reference asserts in similarity_64
+    (LL.cpp:1457); the oracle reports it and the C-ABI refuses the selection (RuntimeError)."""
+    T = [4, 8]
+    bank = synth.synth_bank(4, num_features=150, levels=2, seed=8)
+    tps = bank.classes["01_template"]
+    tps[2][2].features = tps[2][2].features[:10]
+    q, _ = synth.synth_frame(320, 256, levels=2, seed=6)
+    packed = bank.pack(bank.class_ids(), 4)
+    with pytest.raises(RuntimeError):
+        oracle.match(q, T, packed, 80.0)
+    lib = importlib.import_module("6dpose_b200._lib")
+    nat = lib.NativeDetector(T)
+    with pytest.raises(RuntimeError):
+        nat.load_bank(packed, 4)
