@@ -79,6 +79,8 @@ struct lm_detector {
   uint32_t* d_fxy = nullptr;
   uint2* d_fdesc = nullptr;          // lowest-level features, bit-plane addressing
   std::vector<uint8_t> bits_ok;      // per template: the bit-sliced coarse kernel may take it
+  std::vector<uint8_t> safe;         // per template: refinement never skips a feature (LL.cpp:1394)
+  uint8_t* d_safe = nullptr;
   int prep_rows[LM_MAX_LEVELS] = {0}, prep_cols[LM_MAX_LEVELS] = {0};
   bool prepared = false;
   std::vector<TSlot> h_tslot;
@@ -158,7 +160,7 @@ extern "C" void lm_destroy(lm_detector* d) {
   if (d->stream) cudaStreamSynchronize(d->stream);
   for (int l = 0; l < LM_MAX_LEVELS; ++l) free_level(d->lv[l]);
   cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_fdesc); cudaFree(d->d_work);
-  cudaFree(d->d_items_bits); cudaFree(d->d_items_bytes);
+  cudaFree(d->d_items_bits); cudaFree(d->d_items_bytes); cudaFree(d->d_safe);
   cudaFree(d->d_mask); cudaFree(d->d_raw); cudaFree(d->d_cnt); cudaFree(d->d_off);
   cudaFree(d->d_res_own); cudaFree(d->d_counters);
   cudaFreeHost(d->h_counters); cudaFreeHost(d->h_res);
@@ -343,6 +345,33 @@ static int prepare_bank(lm_detector* d) {
       }
       d->bits_ok[g] = (total <= 255 && same) ? 1 : 0;
     }
+  }
+  // "safe" templates: at every refined level the clamp range is regular (max >= border) and every
+  // feature lies inside the template box, so no feature can leave the image once a clamped patch
+  // offset is applied (LL.cpp:1394 never skips) -- the refinement kernel then drops the per-feature test
+  d->safe.assign((size_t)d->G, 0);
+  for (int g = 0; g < d->G; ++g) {
+    bool ok = true;
+    for (int l = 0; l + 1 < d->L && ok; ++l) {
+      const LevelHost& lv = d->lv[l];
+      const int32_t* t0 = &d->tmeta[((size_t)g * d->S + l * d->M) * 4];
+      const int border = 8 * lv.T;
+      ok = lv.cols - t0[0] - border >= border && lv.rows - t0[1] - border >= border;
+      for (int m = 0; m < d->M && ok; ++m) {
+        const int32_t* tm = &d->tmeta[((size_t)g * d->S + l * d->M + m) * 4];
+        for (int k = 0; k < tm[3] && ok; ++k) {
+          const int32_t* f = &d->feats[3 * ((size_t)tm[2] + k)];
+          ok = f[0] <= t0[0] && f[1] <= t0[1];
+        }
+      }
+    }
+    d->safe[g] = ok ? 1 : 0;
+  }
+  cudaFree(d->d_safe);
+  d->d_safe = nullptr;
+  if (d->G) {
+    CU(cudaMalloc(&d->d_safe, (size_t)d->G));
+    CU(cudaMemcpyAsync(d->d_safe, d->safe.data(), (size_t)d->G, cudaMemcpyHostToDevice, d->stream));
   }
   if (nf) {
     CU(cudaMemcpyAsync(d->d_fbase, fbase.data(), nf * 4, cudaMemcpyHostToDevice, d->stream));
@@ -603,6 +632,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     rp.threshold = threshold;
     rp.hdr = d->d_res; rp.capacity = (int32_t)d->res_cap;
     rp.counters = d->d_counters;
+    rp.safe = d->d_safe;
     k_refine<<<d->sm_count * 8, 256, 0, st>>>(rp);
     ++d->launches;
   }

@@ -486,6 +486,8 @@ struct RefineParams {
   lm_result_header* hdr;  // result block: header, then `capacity` records
   int32_t capacity;
   unsigned long long* counters;  // [0] refinement feature-rows processed (x256 = bytes)
+  const uint8_t* safe;           // per template: no feature can leave the image once a clamped patch
+                                 // offset is applied (LL.cpp:1394 never skips) -> 128-bit row loads
 };
 
 __global__ void __launch_bounds__(256) k_refine(RefineParams p) {
@@ -557,6 +559,68 @@ __global__ void __launch_bounds__(256) k_refine(RefineParams p) {
 
       uint32_t s01 = 0, s23 = 0, s45 = 0, s67 = 0;
       int nf2 = 0;
+      if (p.safe[g] && (lv.Wd & 15) == 0) {
+        // Fast path.  Every row of the 16x16 patch starts at the same offset inside its 16-byte
+        // chunk (Wd is a multiple of 16), so the two lanes of a row fetch the two aligned chunks that
+        // hold the row's 16 bytes with ONE 128-bit load each and trade the words they are missing.
+        const uint4* __restrict__ lm128 = reinterpret_cast<const uint4*>(lv.lm);
+        const int shift_row = cy * lv.Wd + cx + row * lv.Wd;
+        const bool hi_half = half != 0;
+        for (int m = 0; m < p.M; ++m) {
+          const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
+          nf2 += ts.y;
+          const uint32_t* __restrict__ fb = p.fbase + ts.x;
+          uint32_t a8 = 0, b8 = 0;
+          int pend = 0;
+          for (int i0 = 0; i0 < ts.y; i0 += 4) {
+            uint32_t a[4];
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              a[u] = __ldg(fb + min(i0 + u, ts.y - 1)) + (uint32_t)shift_row;
+              v[u] = __ldg(lm128 + (a[u] >> 4) + half);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (i0 + u < ts.y) {
+                const uint32_t sh = (a[u] & 3u) << 3;
+                uint32_t w0, w1, w2;
+                switch ((a[u] >> 2) & 3u) {  // warp-uniform: word offset of the row start in its chunk
+                  case 0: {
+                    const uint32_t p2 = __shfl_xor_sync(0xffffffffu, v[u].z, 1);
+                    const uint32_t p3 = __shfl_xor_sync(0xffffffffu, v[u].w, 1);
+                    w0 = hi_half ? p2 : v[u].x; w1 = hi_half ? p3 : v[u].y; w2 = hi_half ? v[u].x : v[u].z;
+                  } break;
+                  case 1: {
+                    const uint32_t p3 = __shfl_xor_sync(0xffffffffu, v[u].w, 1);
+                    w0 = hi_half ? p3 : v[u].y; w1 = hi_half ? v[u].x : v[u].z; w2 = hi_half ? v[u].y : v[u].w;
+                  } break;
+                  case 2: {
+                    const uint32_t p0 = __shfl_xor_sync(0xffffffffu, v[u].x, 1);
+                    w0 = hi_half ? v[u].x : v[u].z; w1 = hi_half ? v[u].y : v[u].w; w2 = hi_half ? v[u].z : p0;
+                  } break;
+                  default: {
+                    const uint32_t p0 = __shfl_xor_sync(0xffffffffu, v[u].x, 1);
+                    const uint32_t p1 = __shfl_xor_sync(0xffffffffu, v[u].y, 1);
+                    w0 = hi_half ? v[u].y : v[u].w; w1 = hi_half ? v[u].z : p0; w2 = hi_half ? v[u].w : p1;
+                  } break;
+                }
+                a8 += __funnelshift_r(w0, w1, sh);
+                b8 += __funnelshift_r(w1, w2, sh);
+                if (++pend == 63) {
+                  s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
+                  s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
+                  a8 = b8 = 0;
+                  pend = 0;
+                }
+              }
+            }
+          }
+          s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
+          s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
+          feats_done += ts.y;
+        }
+      } else
       for (int m = 0; m < p.M; ++m) {
         const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
         nf2 += ts.y;
