@@ -81,6 +81,7 @@ struct lm_detector {
   std::vector<uint8_t> bits_ok;      // per template: the bit-sliced coarse kernel may take it
   std::vector<uint8_t> safe;         // per template: refinement never skips a feature (LL.cpp:1394)
   uint8_t* d_safe = nullptr;
+  uint16_t* d_galign = nullptr;      // [G][S][16] feature counts per (address & 15) group
   int prep_rows[LM_MAX_LEVELS] = {0}, prep_cols[LM_MAX_LEVELS] = {0};
   bool prepared = false;
   std::vector<TSlot> h_tslot;
@@ -160,7 +161,7 @@ extern "C" void lm_destroy(lm_detector* d) {
   if (d->stream) cudaStreamSynchronize(d->stream);
   for (int l = 0; l < LM_MAX_LEVELS; ++l) free_level(d->lv[l]);
   cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_fdesc); cudaFree(d->d_work);
-  cudaFree(d->d_items_bits); cudaFree(d->d_items_bytes); cudaFree(d->d_safe);
+  cudaFree(d->d_items_bits); cudaFree(d->d_items_bytes); cudaFree(d->d_safe); cudaFree(d->d_galign);
   cudaFree(d->d_mask); cudaFree(d->d_raw); cudaFree(d->d_cnt); cudaFree(d->d_off);
   cudaFree(d->d_res_own); cudaFree(d->d_counters);
   cudaFreeHost(d->h_counters); cudaFreeHost(d->h_res);
@@ -366,6 +367,31 @@ static int prepare_bank(lm_detector* d) {
       }
     }
     d->safe[g] = ok ? 1 : 0;
+  }
+  // refined levels: store each template's features grouped by (address & 15) -- sums do not depend
+  // on the order, and the refinement kernel then knows the row alignment of a whole group at once
+  std::vector<uint16_t> galign((size_t)d->G * d->S * 16, 0);
+  for (int g = 0; g < d->G; ++g)
+    for (int s = 0; s < d->S - d->M; ++s) {  // every slot above the lowest level
+      const int32_t* tm = &d->tmeta[((size_t)g * d->S + s) * 4];
+      const size_t b0 = (size_t)tm[2];
+      const int n = tm[3];
+      std::vector<int> order(n);
+      for (int k = 0; k < n; ++k) order[k] = k;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (fbase[b0 + a] & 15u) < (fbase[b0 + b] & 15u); });
+      std::vector<uint32_t> tb(n), tx(n);
+      for (int k = 0; k < n; ++k) {
+        tb[k] = fbase[b0 + order[k]];
+        tx[k] = fxy[b0 + order[k]];
+        ++galign[((size_t)g * d->S + s) * 16 + (tb[k] & 15u)];
+      }
+      for (int k = 0; k < n; ++k) { fbase[b0 + k] = tb[k]; fxy[b0 + k] = tx[k]; }
+    }
+  cudaFree(d->d_galign);
+  d->d_galign = nullptr;
+  if (!galign.empty()) {
+    CU(cudaMalloc(&d->d_galign, galign.size() * sizeof(uint16_t)));
+    CU(cudaMemcpyAsync(d->d_galign, galign.data(), galign.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, d->stream));
   }
   cudaFree(d->d_safe);
   d->d_safe = nullptr;
@@ -632,7 +658,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     rp.threshold = threshold;
     rp.hdr = d->d_res; rp.capacity = (int32_t)d->res_cap;
     rp.counters = d->d_counters;
-    rp.safe = d->d_safe;
+    rp.safe = d->d_safe; rp.galign = d->d_galign;
     k_refine<<<d->sm_count * 8, 256, 0, st>>>(rp);
     ++d->launches;
   }

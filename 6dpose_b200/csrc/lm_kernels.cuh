@@ -488,9 +488,43 @@ struct RefineParams {
   unsigned long long* counters;  // [0] refinement feature-rows processed (x256 = bytes)
   const uint8_t* safe;           // per template: no feature can leave the image once a clamped patch
                                  // offset is applied (LL.cpp:1394 never skips) -> 128-bit row loads
+  const uint16_t* galign;        // [G][S][16]: features per (fbase & 15) group (refined levels are stored
+                                 // grouped by it)
 };
 
-__global__ void __launch_bounds__(256) k_refine(RefineParams p) {
+// One lane pair = one row of the 16x16 patch: lane `half` loads the aligned 16-byte chunk (a >> 4) +
+// half; K = word offset of the row start inside the first chunk.  The lane then needs the words
+// K + 2*half .. K + 2*half + 2 of the 8-word pair and gets the ones it lacks from its partner.
+template <int K>
+__device__ __forceinline__ void refine_rows(const uint4* __restrict__ lm128, const uint32_t* __restrict__ fb, int n,
+                                            uint32_t shift_row, int half, uint32_t sh, uint32_t& a8, uint32_t& b8) {
+  const bool hi = half != 0;
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) {
+    const uint32_t a = __ldg(fb + i) + shift_row;
+    const uint4 v = __ldg(lm128 + (a >> 4) + half);
+    uint32_t w0, w1, w2;
+    if (K == 0) {
+      const uint32_t p2 = __shfl_xor_sync(0xffffffffu, v.z, 1);
+      const uint32_t p3 = __shfl_xor_sync(0xffffffffu, v.w, 1);
+      w0 = hi ? p2 : v.x; w1 = hi ? p3 : v.y; w2 = hi ? v.x : v.z;
+    } else if (K == 1) {
+      const uint32_t p3 = __shfl_xor_sync(0xffffffffu, v.w, 1);
+      w0 = hi ? p3 : v.y; w1 = hi ? v.x : v.z; w2 = hi ? v.y : v.w;
+    } else if (K == 2) {
+      const uint32_t p0 = __shfl_xor_sync(0xffffffffu, v.x, 1);
+      w0 = hi ? v.x : v.z; w1 = hi ? v.y : v.w; w2 = hi ? v.z : p0;
+    } else {
+      const uint32_t p0 = __shfl_xor_sync(0xffffffffu, v.x, 1);
+      const uint32_t p1 = __shfl_xor_sync(0xffffffffu, v.y, 1);
+      w0 = hi ? v.y : v.w; w1 = hi ? v.z : p0; w2 = hi ? v.w : p1;
+    }
+    a8 += __funnelshift_r(w0, w1, sh);
+    b8 += __funnelshift_r(w1, w2, sh);
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) k_refine(RefineParams p) {
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int total = p.off[p.n_work];
@@ -563,56 +597,37 @@ __global__ void __launch_bounds__(256) k_refine(RefineParams p) {
         // Fast path.  Every row of the 16x16 patch starts at the same offset inside its 16-byte
         // chunk (Wd is a multiple of 16), so the two lanes of a row fetch the two aligned chunks that
         // hold the row's 16 bytes with ONE 128-bit load each and trade the words they are missing.
+        // The features of a template are stored grouped by (address & 15), so the word offset of the
+        // row start (which decides who trades what) is constant over a whole group of features.
         const uint4* __restrict__ lm128 = reinterpret_cast<const uint4*>(lv.lm);
-        const int shift_row = cy * lv.Wd + cx + row * lv.Wd;
-        const bool hi_half = half != 0;
+        const uint32_t shift_row = (uint32_t)(cy * lv.Wd + cx + row * lv.Wd);
         for (int m = 0; m < p.M; ++m) {
           const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
           nf2 += ts.y;
           const uint32_t* __restrict__ fb = p.fbase + ts.x;
+          const uint16_t* __restrict__ ga = p.galign + ((size_t)g * p.S + l * p.M + m) * 16;
           uint32_t a8 = 0, b8 = 0;
           int pend = 0;
-          for (int i0 = 0; i0 < ts.y; i0 += 4) {
-            uint32_t a[4];
-            uint4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              a[u] = __ldg(fb + min(i0 + u, ts.y - 1)) + (uint32_t)shift_row;
-              v[u] = __ldg(lm128 + (a[u] >> 4) + half);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (i0 + u < ts.y) {
-                const uint32_t sh = (a[u] & 3u) << 3;
-                uint32_t w0, w1, w2;
-                switch ((a[u] >> 2) & 3u) {  // warp-uniform: word offset of the row start in its chunk
-                  case 0: {
-                    const uint32_t p2 = __shfl_xor_sync(0xffffffffu, v[u].z, 1);
-                    const uint32_t p3 = __shfl_xor_sync(0xffffffffu, v[u].w, 1);
-                    w0 = hi_half ? p2 : v[u].x; w1 = hi_half ? p3 : v[u].y; w2 = hi_half ? v[u].x : v[u].z;
-                  } break;
-                  case 1: {
-                    const uint32_t p3 = __shfl_xor_sync(0xffffffffu, v[u].w, 1);
-                    w0 = hi_half ? p3 : v[u].y; w1 = hi_half ? v[u].x : v[u].z; w2 = hi_half ? v[u].y : v[u].w;
-                  } break;
-                  case 2: {
-                    const uint32_t p0 = __shfl_xor_sync(0xffffffffu, v[u].x, 1);
-                    w0 = hi_half ? v[u].x : v[u].z; w1 = hi_half ? v[u].y : v[u].w; w2 = hi_half ? v[u].z : p0;
-                  } break;
-                  default: {
-                    const uint32_t p0 = __shfl_xor_sync(0xffffffffu, v[u].x, 1);
-                    const uint32_t p1 = __shfl_xor_sync(0xffffffffu, v[u].y, 1);
-                    w0 = hi_half ? v[u].y : v[u].w; w1 = hi_half ? v[u].z : p0; w2 = hi_half ? v[u].w : p1;
-                  } break;
-                }
-                a8 += __funnelshift_r(w0, w1, sh);
-                b8 += __funnelshift_r(w1, w2, sh);
-                if (++pend == 63) {
-                  s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
-                  s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
-                  a8 = b8 = 0;
-                  pend = 0;
-                }
+          for (int grp = 0; grp < 16; ++grp) {
+            int n = ga[grp];
+            const uint32_t o = ((uint32_t)grp + shift_row) & 15u;
+            const uint32_t sh = (o & 3u) << 3;
+            while (n > 0) {
+              const int take = min(n, 63 - pend);
+              switch (o >> 2) {
+                case 0: refine_rows<0>(lm128, fb, take, shift_row, half, sh, a8, b8); break;
+                case 1: refine_rows<1>(lm128, fb, take, shift_row, half, sh, a8, b8); break;
+                case 2: refine_rows<2>(lm128, fb, take, shift_row, half, sh, a8, b8); break;
+                default: refine_rows<3>(lm128, fb, take, shift_row, half, sh, a8, b8); break;
+              }
+              fb += take;
+              n -= take;
+              pend += take;
+              if (pend == 63) {  // 63 * 4 = 252: no carry between packed bytes
+                s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
+                s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
+                a8 = b8 = 0;
+                pend = 0;
               }
             }
           }
