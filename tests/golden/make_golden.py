@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.npz from the reference's own fixtures (needs /root/reference mounted
+and oracle/_ref built: `make -C oracle ref`).
+
+Inputs : linemodLevelup/test/case1/0000_{rgb,dep}.png (+ _half), banks 63/, 127/, allScales/
+         (reference: linemodLevelup/test.cpp:90-128, 174-181 -- the invocations the reference's own
+         test driver makes: Detector(127,{5,8}) + thr 75, Detector() + allScales + thr 80).
+Stored : the quantized label pyramids produced by 6dpose_b200/frontend.py (so the GPU box needs no
+         reference checkout), the packed template banks, and the expected match lists computed by the
+         REFERENCE'S OWN CODE (oracle/_ref = linemodLevelup.cpp compiled unmodified).
+"""
+import importlib
+import os
+import sys
+
+import cv2
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+CASE = "/root/reference/linemodLevelup/test/case1/"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    fe = importlib.import_module("6dpose_b200.frontend")
+    bk = importlib.import_module("6dpose_b200.bank")
+    from oracle import oracle, ref
+    assert ref.build(), "oracle/_ref could not be built (is /root/reference mounted?)"
+
+    frames = {}
+    for tag, suffix in (("full", ""), ("half", "_half")):
+        rgb = cv2.imread(CASE + "0000_rgb%s.png" % suffix)  # BGR, as cv::imread in test.cpp:90
+        dep = cv2.imread(CASE + "0000_dep%s.png" % suffix, cv2.IMREAD_UNCHANGED)
+        q = fe.quantize_pyramid([rgb, dep], 2)
+        frames[tag] = q
+    np.savez_compressed(os.path.join(OUT, "frames_case1.npz"),
+                        **{"%s_l%d_m%d" % (tag, l, m): frames[tag][l][m] for tag in frames for l in range(2) for m in range(2)})
+
+    cases = []
+    for bank_name, limit, T, thresholds in (("127", None, [5, 8], (75.0, 60.0)), ("63", None, [5, 8], (75.0, 60.0)),
+                                           ("allScales", 7, [5, 8], (75.0, 65.0))):
+        b = bk.TemplateBank()
+        b.read_class(CASE + bank_name + "/06_template.yaml", 2)
+        if limit:  # every limit-th template of the 2989 (all radii 600..1800 mm stay represented)
+            b.classes["06_template"] = b.classes["06_template"][::limit]
+        packed = b.pack(b.class_ids(), 4)
+        np.savez_compressed(os.path.join(OUT, "bank_%s.npz" % bank_name), class_begin=packed["class_begin"],
+                            tmeta=packed["tmeta"], feats=packed["feats"].astype(np.int16), T=np.asarray(T, np.int32))
+        for tag in frames:
+            for thr in thresholds:
+                want = ref.match(frames[tag], T, packed, thr)
+                again = oracle.match(frames[tag], T, packed, thr)
+                assert np.array_equal(want, again), "restatement and reference disagree"
+                key = "%s_%s_%g" % (bank_name, tag, thr)
+                cases.append((key, want))
+                print(key, len(want), want[:2])
+    np.savez_compressed(os.path.join(OUT, "expected_case1.npz"), **{k: v for k, v in cases})
+
+
+if __name__ == "__main__":
+    main()
