@@ -23,6 +23,7 @@ SYMBOLS = [
     "lm_upload_quantized", "lm_bind_quantized_device", "lm_run", "lm_enqueue", "lm_complete", "lm_set_result_buffer", "lm_device_result", "lm_fetch_records",
     "lm_finish", "lm_match_quantized", "lm_debug_linear_memories", "lm_counters", "lm_set_timing",
     "lm_stage_times", "lm_stream", "lm_launch_count",
+    "lm_icp_create", "lm_icp_destroy", "lm_icp_process", "lm_icp_process_batch", "lm_icp_last_stats", "lm_icp_launch_count", "lm_icp_set_use_scene_cloud",
 ]
 
 _lib = None
@@ -71,6 +72,19 @@ def load():
     L.lm_stream.restype = vp
     L.lm_launch_count.argtypes = [vp]
     L.lm_launch_count.restype = c_i64
+    f32p, f64p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+    u16p = ctypes.POINTER(ctypes.c_uint16)
+    L.lm_icp_create.argtypes = [c_int, ctypes.POINTER(vp)]
+    L.lm_icp_destroy.argtypes = [vp]
+    L.lm_icp_destroy.restype = None
+    L.lm_icp_process.argtypes = [vp, u16p, c_int, c_int, u16p, c_int, c_int, f32p, f32p, f32p, f32p, c_int, c_int, c_int,
+                                 f64p, f64p, f32p]
+    L.lm_icp_process_batch.argtypes = [vp, c_int, u16p, c_int, c_int, ctypes.POINTER(u16p), c_int, c_int, f32p, f32p, f32p, f32p,
+                                       i32p, c_int, f64p, f64p, f32p]
+    L.lm_icp_last_stats.argtypes = [vp, f64p]
+    L.lm_icp_set_use_scene_cloud.argtypes = [vp, c_int]
+    L.lm_icp_launch_count.argtypes = [vp]
+    L.lm_icp_launch_count.restype = c_i64
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError if the library does not export a declared symbol
     _lib = L
@@ -242,3 +256,64 @@ class NativeDetector:
 
     def launch_count(self):
         return int(self._L.lm_launch_count(self._h))
+
+
+class NativeIcp:
+    """RAII wrapper over the lm_icp handle (poseRefine compute)."""
+
+    def __init__(self, device=0):
+        L = load()
+        self._L = L
+        h = ctypes.c_void_p()
+        check(L.lm_icp_create(int(device), ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lm_icp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process_batch(self, scene_depth, model_depths, sceneK, modelKs, Rs, ts, detect_xy, max_iterations=30):
+        """scene u16 HxW; model_depths list of u16 HxW (same size); modelKs/Rs [n,3,3] f32; ts [n,3] f32;
+        detect_xy [n,2] int.  Returns (R [n,3,3] f64, t [n,3] f64 mm, residual [n] f32)."""
+        n = len(model_depths)
+        scene = np.ascontiguousarray(scene_depth, np.uint16)
+        models = [np.ascontiguousarray(m, np.uint16) for m in model_depths]
+        for m in models:
+            if m.shape != models[0].shape:
+                raise TypeError("model depth images must share one size")
+        u16p = ctypes.POINTER(ctypes.c_uint16)
+        f32p, f64p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+        mp = (u16p * max(n, 1))(*[m.ctypes.data_as(u16p) for m in models])
+        sK = np.ascontiguousarray(sceneK, np.float32).reshape(9)
+        mK = np.ascontiguousarray(modelKs, np.float32).reshape(n, 9)
+        R = np.ascontiguousarray(Rs, np.float32).reshape(n, 9)
+        t = np.ascontiguousarray(ts, np.float32).reshape(n, 3)
+        xy = np.ascontiguousarray(detect_xy, np.int32).reshape(n, 2)
+        Ro = np.full((n, 3, 3), np.nan, np.float64)
+        to = np.full((n, 3), np.nan, np.float64)
+        res = np.zeros(n, np.float32)
+        mrows, mcols = (models[0].shape if n else (1, 1))
+        check(self._L.lm_icp_process_batch(self._h, n, scene.ctypes.data_as(u16p), scene.shape[0], scene.shape[1], mp, mrows, mcols,
+                                           sK.ctypes.data_as(f32p), mK.ctypes.data_as(f32p), R.ctypes.data_as(f32p),
+                                           t.ctypes.data_as(f32p), xy.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                           int(max_iterations), Ro.ctypes.data_as(f64p), to.ctypes.data_as(f64p),
+                                           res.ctypes.data_as(f32p)))
+        return Ro, to, res
+
+    def set_use_scene_cloud(self, on):
+        check(self._L.lm_icp_set_use_scene_cloud(self._h, 1 if on else 0))
+
+    def last_stats(self):
+        a = (ctypes.c_double * 4)()
+        check(self._L.lm_icp_last_stats(self._h, a))
+        return dict(points=int(a[0]), iterations=int(a[1]), rmse=float(a[2]), kernel_us=float(a[3]))
+
+    def launch_count(self):
+        return int(self._L.lm_icp_launch_count(self._h))

@@ -42,6 +42,15 @@ static int fail(int code, const char* fmt, ...) {
 
 extern "C" const char* lm_last_error(void) { return g_err; }
 
+// shared with lm_icp.cu
+int lm_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
 #include "lm_kernels.cuh"
 
 // --------------------------------------------------------------------------------------------

@@ -143,6 +143,38 @@ void* lm_stream(lm_detector* d);
 /* Number of kernel launches issued by this handle since creation. */
 int64_t lm_launch_count(lm_detector* d);
 
+/* ---- poseRefine (reference: linemodLevelup/linemodLevelup.h:8-19, linemodLevelup.cpp:27-155) ---- */
+typedef struct lm_icp lm_icp; /* replaces class poseRefine's compute; the R/t/residual state lives in the caller */
+
+int lm_icp_create(int device, lm_icp** out);
+void lm_icp_destroy(lm_icp* h);
+
+/* poseRefine::process.  sceneDepth / modelDepth: u16 millimetres, row-major; sceneK / modelK / R: 9 floats
+ * row-major; t: 3 floats (mm); detectX/Y: the match position.  max_iterations: Open3D's
+ * ICPConvergenceCriteria::max_iteration_ (the reference uses the default, 30).  Outputs: R_out 9
+ * doubles row-major (getR), t_out 3 doubles in mm (getT), residual = ICP fitness (getResidual), or -1
+ * with R_out/t_out untouched when the model box does not fit the scene at the match position
+ * (early return, LL.cpp:52-55). */
+int lm_icp_process(lm_icp* h, const uint16_t* scene_depth, int srows, int scols, const uint16_t* model_depth, int mrows,
+                   int mcols, const float* sceneK, const float* modelK, const float* R, const float* t, int detectX,
+                   int detectY, int max_iterations, double* R_out, double* t_out, float* residual);
+
+/* The same for n hypotheses against one scene image in one launch (what the callers do for the top
+ * matches after NMS, linemod_and_levelup_test.py:351-367): model_depths[i], modelK + 9i, R + 9i,
+ * t + 3i, detect_xy[2i..2i+1]; outputs R_out + 9i, t_out + 3i, residual[i]. */
+int lm_icp_process_batch(lm_icp* h, int n_hyp, const uint16_t* scene_depth, int srows, int scols,
+                         const uint16_t* const* model_depths, int mrows, int mcols, const float* sceneK, const float* modelK,
+                         const float* R, const float* t, const int32_t* detect_xy, int max_iterations, double* R_out,
+                         double* t_out, float* residual);
+
+/* Of the last hypothesis processed: [0] points in the down-sampled cloud, [1] ICP iterations run,
+ * [2] inlier rmse (m), [3] device time of the normals + ICP kernels of the last call (us). */
+int lm_icp_last_stats(lm_icp* h, double* out4);
+/* NOT the reference's behaviour (default off): register the model cloud against the down-sampled SCENE
+ * cloud, which is what LL.cpp:109 evidently meant to do (it down-samples the model cloud twice). */
+int lm_icp_set_use_scene_cloud(lm_icp* h, int on);
+int64_t lm_icp_launch_count(lm_icp* h);
+
 #ifdef __cplusplus
 }
 #endif
