@@ -144,6 +144,15 @@ extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** o
   if (n_levels < 1 || n_levels > LM_MAX_LEVELS) return fail(LM_E_INVALID, "pyramid levels must be 1..%d", LM_MAX_LEVELS);
   for (int l = 0; l < n_levels; ++l)
     if (T[l] < 1 || T[l] > 16) return fail(LM_E_INVALID, "T[%d]=%d outside 1..16", l, T[l]);
+  if (device == -1) {
+    // host-only handle: bank / selection / shard ranges / lm_finish work, every GPU stage refuses to run
+    lm_detector* d = new lm_detector();
+    d->device = -1;
+    d->L = n_levels;
+    for (int l = 0; l < n_levels; ++l) d->T[l] = T[l];
+    *out = d;
+    return LM_OK;
+  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -166,6 +175,7 @@ extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** o
 
 extern "C" void lm_destroy(lm_detector* d) {
   if (!d) return;
+  if (d->device < 0) { delete d; return; }
   cudaSetDevice(d->device);
   if (d->stream) cudaStreamSynchronize(d->stream);
   for (int l = 0; l < LM_MAX_LEVELS; ++l) free_level(d->lv[l]);
@@ -211,7 +221,7 @@ extern "C" int lm_load_bank(lm_detector* d, int n_classes, const int32_t* class_
         slot_of[(size_t)m4[2] + i] = (uint8_t)s;
       }
     }
-  CU(cudaSetDevice(d->device));
+  if (d->device >= 0) CU(cudaSetDevice(d->device));
   d->n_classes = n_classes;
   d->S = n_slots;
   d->G = G;
@@ -221,8 +231,8 @@ extern "C" int lm_load_bank(lm_detector* d, int n_classes, const int32_t* class_
   d->feat_slot.swap(slot_of);
   cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_fdesc);
   d->d_tslot = nullptr; d->d_fbase = nullptr; d->d_fxy = nullptr; d->d_fdesc = nullptr;
-  if (G > 0) CU(cudaMalloc(&d->d_tslot, sizeof(TSlot) * (size_t)G * n_slots));
-  if (n_feats > 0) {
+  if (d->device >= 0 && G > 0) CU(cudaMalloc(&d->d_tslot, sizeof(TSlot) * (size_t)G * n_slots));
+  if (d->device >= 0 && n_feats > 0) {
     CU(cudaMalloc(&d->d_fbase, sizeof(uint32_t) * (size_t)n_feats));
     CU(cudaMalloc(&d->d_fxy, sizeof(uint32_t) * (size_t)n_feats));
     CU(cudaMalloc(&d->d_fdesc, sizeof(uint2) * (size_t)n_feats));
@@ -525,6 +535,7 @@ static int size_levels(lm_detector* d, const int* rows, const int* cols, bool ne
 }
 
 extern "C" int lm_upload_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols) {
+  if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
   if (!d || !quantized || !rows || !cols) return fail(LM_E_INVALID, "null argument");
   CU(cudaSetDevice(d->device));
   int rc = check_frame_dims(d, rows, cols);
@@ -547,6 +558,7 @@ extern "C" int lm_upload_quantized(lm_detector* d, const uint8_t* const* quantiz
 }
 
 extern "C" int lm_bind_quantized_device(lm_detector* d, const uint8_t* const* d_quantized, const int* rows, const int* cols) {
+  if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
   if (!d || !d_quantized || !rows || !cols) return fail(LM_E_INVALID, "null argument");
   CU(cudaSetDevice(d->device));
   int rc = check_frame_dims(d, rows, cols);
@@ -723,6 +735,7 @@ static int ensure_run_buffers(lm_detector* d) {
 }
 
 extern "C" int lm_enqueue(lm_detector* d, float threshold) {
+  if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
   if (!d) return fail(LM_E_INVALID, "null detector");
   if (!d->have_frame) return fail(LM_E_STATE, "no frame uploaded");
   if (d->S == 0) return fail(LM_E_STATE, "no template bank loaded");
@@ -738,6 +751,7 @@ extern "C" int lm_enqueue(lm_detector* d, float threshold) {
 }
 
 extern "C" int lm_complete(lm_detector* d) {
+  if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
   if (!d) return fail(LM_E_INVALID, "null detector");
   CU(cudaSetDevice(d->device));
   int rc = enqueue_readback(d);
@@ -773,6 +787,7 @@ extern "C" int lm_run(lm_detector* d, float threshold) {
 }
 
 extern "C" int lm_set_result_buffer(lm_detector* d, void* d_block, int64_t capacity_records) {
+  if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
   if (!d) return fail(LM_E_INVALID, "null detector");
   if (d_block && capacity_records < 1) return fail(LM_E_INVALID, "capacity must be >= 1");
   if (capacity_records > 0x7FFFFFFF) return fail(LM_E_INVALID, "capacity too large");
@@ -902,6 +917,7 @@ extern "C" int lm_counters(lm_detector* d, int64_t* out5) {
 }
 
 extern "C" int lm_set_timing(lm_detector* d, int slots) {
+  if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
   if (!d) return fail(LM_E_INVALID, "null detector");
   CU(cudaSetDevice(d->device));
   CU(cudaStreamSynchronize(d->stream));

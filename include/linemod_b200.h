@@ -62,7 +62,9 @@ typedef struct lm_result_header {
 const char* lm_last_error(void);
 
 /* Detector(num_features, T) / Detector(T) / Detector(): LL.cpp:1663-1692.  `T` has n_levels entries
- * (sampling step per pyramid level).  `device` is the CUDA ordinal. */
+ * (sampling step per pyramid level).  `device` is the CUDA ordinal; -1 creates a host-only handle that
+ * can hold a bank, compute selections / shard ranges and run lm_finish (the merge step of a multi-GPU
+ * match) but refuses every GPU stage with LM_E_STATE. */
 int lm_create(int device, int n_levels, const int* T, lm_detector** out);
 void lm_destroy(lm_detector* d);
 

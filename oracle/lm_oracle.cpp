@@ -416,9 +416,9 @@ int lmo_linear_memories(const uint8_t* quantized, int rows, int cols, int T, uin
 //   stats[8] (optional): coarse_byte_adds, refine_byte_adds, coarse_candidates, pre-unique matches,
 //                        t_linmem_us, t_match_us, t_sort_us, threads used
 // Returns the number of matches (may exceed cap: only cap are written), or <0 on error.
-long lmo_match(int L, int M, const int* T, const int* rows, const int* cols, const uint8_t* const* quantized,
-               int n_classes, const int* class_begin, const int32_t* tmeta, const int32_t* feats,
-               float threshold, int n_threads, lmo_match_rec* out, long cap, double* stats) {
+static long match_impl(int L, int M, const int* T, const int* rows, const int* cols, const uint8_t* const* quantized,
+                       int n_classes, const int* class_begin, const int32_t* tmeta, const int32_t* feats,
+                       float threshold, int n_threads, lmo_match_rec* out, long cap, double* stats, bool finish) {
   typedef std::chrono::steady_clock clk;
   for (int l = 0; l < L; ++l)
     if (T[l] <= 0 || rows[l] % T[l] || cols[l] % T[l] || ((long)rows[l] * cols[l]) % 16) return -2;
@@ -477,9 +477,10 @@ long lmo_match(int L, int M, const int* T, const int* rows, const int* cols, con
   for (int g = 0; g < G; ++g) all.insert(all.end(), per[g].begin(), per[g].end());
   auto t2 = clk::now();
   const size_t pre_unique = all.size();
-  // LL.cpp:1772-1774
-  std::sort(all.begin(), all.end());
-  all.erase(std::unique(all.begin(), all.end()), all.end());
+  if (finish) {  // LL.cpp:1772-1774
+    std::sort(all.begin(), all.end());
+    all.erase(std::unique(all.begin(), all.end()), all.end());
+  }
   auto t3 = clk::now();
 
   const long n = (long)all.size();
@@ -501,6 +502,20 @@ long lmo_match(int L, int M, const int* T, const int* rows, const int* cols, con
     stats[4] = us(t0, t1); stats[5] = us(t1, t2); stats[6] = us(t2, t3); stats[7] = used_threads;
   }
   return n;
+}
+
+long lmo_match(int L, int M, const int* T, const int* rows, const int* cols, const uint8_t* const* quantized,
+               int n_classes, const int* class_begin, const int32_t* tmeta, const int32_t* feats,
+               float threshold, int n_threads, lmo_match_rec* out, long cap, double* stats) {
+  return match_impl(L, M, T, rows, cols, quantized, n_classes, class_begin, tmeta, feats, threshold, n_threads, out, cap, stats, true);
+}
+
+// The same, stopped before std::sort/std::unique: the matches in the reference's pre-sort order
+// (class order -> template_id -> ascending coarse cell).  Used by the sharding tests.
+long lmo_match_presort(int L, int M, const int* T, const int* rows, const int* cols, const uint8_t* const* quantized,
+                       int n_classes, const int* class_begin, const int32_t* tmeta, const int32_t* feats,
+                       float threshold, int n_threads, lmo_match_rec* out, long cap, double* stats) {
+  return match_impl(L, M, T, rows, cols, quantized, n_classes, class_begin, tmeta, feats, threshold, n_threads, out, cap, stats, false);
 }
 
 // Debug/inspection: the coarse total_similarity map (u16, Hd*Wd) of one

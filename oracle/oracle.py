@@ -52,6 +52,8 @@ def lib():
                                 ctypes.c_int, i32p, i32p, i32p, ctypes.c_float, ctypes.c_int,
                                 ctypes.POINTER(MatchRec), ctypes.c_long, ctypes.POINTER(ctypes.c_double)]
         L.lmo_match.restype = ctypes.c_long
+        L.lmo_match_presort.argtypes = L.lmo_match.argtypes
+        L.lmo_match_presort.restype = ctypes.c_long
         L.lmo_coarse_map.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(u8p),
                                      i32p, i32p, ctypes.POINTER(ctypes.c_uint16)]
         L.lmo_coarse_map.restype = ctypes.c_long
@@ -99,7 +101,7 @@ def linear_memories(q, T):
     return out
 
 
-def match(quantized, T, packed, threshold, n_threads=1, cap=None, want_stats=False):
+def match(quantized, T, packed, threshold, n_threads=1, cap=None, want_stats=False, presort=False):
     """quantized: list over levels of list over modalities of u8 HxW; packed: TemplateBank.pack() dict.
 
     Returns a structured array (REC_DTYPE) in the reference's final order (+ stats dict)."""
@@ -116,7 +118,8 @@ def match(quantized, T, packed, threshold, n_threads=1, cap=None, want_stats=Fal
     stats = (ctypes.c_double * 8)()
     while True:
         out = np.zeros(cap, REC_DTYPE)
-        n = lib().lmo_match(L, M, _i32(Ts), _i32(rows), _i32(cols), ptrs, len(cb) - 1, _i32(cb), _i32(tm), _i32(ft),
+        fn = lib().lmo_match_presort if presort else lib().lmo_match
+        n = fn(L, M, _i32(Ts), _i32(rows), _i32(cols), ptrs, len(cb) - 1, _i32(cb), _i32(tm), _i32(ft),
                             ctypes.c_float(threshold), int(n_threads),
                             out.ctypes.data_as(ctypes.POINTER(MatchRec)), cap, stats)
         if n < 0:
