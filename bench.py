@@ -116,61 +116,56 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_fps(args, bank, frames, n_frames, threads):
-    """The reference's CPU algorithm (oracle port, or oracle/_ref when built) on the host cores."""
+def cpu_arms(args, bank, frames, n_frames):
+    """The reference's algorithm on the host cores, two ways: oracle/_ref = the reference's own
+    linemodLevelup.cpp compiled unmodified (single-threaded, like the reference), and the OpenMP-over-
+    templates port in oracle/lm_oracle.cpp on every core.  Returns a dict of fps per arm."""
     from oracle import oracle
     packed = bank.pack(bank.class_ids(), 4)
-    kind = "port"
-    run = lambda q: oracle.match(q, T_PYR, packed, args.threshold, n_threads=threads)
+    threads = os.cpu_count() or 1
+    arms = {"port_all_cores": (lambda q: oracle.match(q, T_PYR, packed, args.threshold, n_threads=threads), threads),
+            "port_1_thread": (lambda q: oracle.match(q, T_PYR, packed, args.threshold, n_threads=1), 1)}
     try:
         from oracle import ref as oref
         if oref.available():
-            kind = "reference"
-            run = lambda q: oref.match(q, T_PYR, packed, args.threshold, n_threads=threads)
+            arms["reference_1_thread"] = (lambda q: oref.match(q, T_PYR, packed, args.threshold), 1)
     except ImportError:
         pass
-    run(frames[0])  # warm-up (page in, thread pool)
-    t0 = time.perf_counter()
-    n = 0
-    for i in range(n_frames):
-        r = run(frames[i % len(frames)])
-        n += 1
-    dt = time.perf_counter() - t0
-    return n / dt, kind, dt, len(r)
+    out = {}
+    for name, (fn, cores) in arms.items():
+        fn(frames[0])  # warm-up (page in, thread pool)
+        t0 = time.perf_counter()
+        for i in range(n_frames):
+            fn(frames[i % len(frames)])
+        dt = time.perf_counter() - t0
+        out[name] = {"fps": n_frames / dt, "cores": cores, "seconds": dt}
+    return out
+
+
+def best_cpu_arm(arms):
+    name = max(arms, key=lambda k: arms[k]["fps"])
+    kind = "reference" if name.startswith("reference") else "port"
+    return name, kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    n_frames = min(max(args.steps + args.warmup, 1), 64)
+    n_frames = min(max(args.steps, 1), 32)  # a bounded sample of full frames: the whole run stays within minutes
     bank, frames = make_workload(args, min(n_frames, 8))
-    from oracle import oracle
-    packed = bank.pack(bank.class_ids(), 4)
-    kind = "port"
-    fn = oracle.match
-    try:
-        from oracle import ref as oref
-        if oref.available():
-            kind, fn = "reference", oref.match
-    except ImportError:
-        pass
-    for i in range(args.warmup):
-        fn(frames[i % len(frames)], T_PYR, packed, args.threshold, n_threads=threads)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        fn(frames[i % len(frames)], T_PYR, packed, args.threshold, n_threads=threads)
-    dt = time.perf_counter() - t0
-    fps = args.steps / dt
+    arms = cpu_arms(args, bank, frames, n_frames)
+    name, kind = best_cpu_arm(arms)
+    fps = arms[name]["fps"]
     out = {
         "impl": "reference", "metric": "frames/sec @640x480, 3115-template bank, Detector::match after quantization",
-        "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": n_frames, "warmup": 1,
+        "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8/u16", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
-                         "sample": "%d full frames of the same workload, OpenMP over templates" % args.steps},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": arms[name]["cores"], "kind": kind,
+                         "sample": "%d full frames of the same workload per arm; fastest arm reported (%s)" % (n_frames, name),
+                         "arms": arms},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
@@ -359,10 +354,11 @@ def main():
         "counters": counters,
     }
     if not args.no_cpu_baseline and world == 1:
-        threads = os.cpu_count() or 1
-        v, kind, dt_cpu, nm = cpu_reference_fps(args, bank, frames, args.cpu_frames, threads)
-        out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": threads, "kind": kind,
-                               "sample": "%d full frames of the same workload in %.1f s, OpenMP over templates" % (args.cpu_frames, dt_cpu)}
+        arms = cpu_arms(args, bank, frames, args.cpu_frames)
+        name, kind = best_cpu_arm(arms)
+        out["cpu_baseline"] = {"value": arms[name]["fps"], "unit": "frames/s", "cores": arms[name]["cores"], "kind": kind,
+                               "sample": "%d full frames of the same workload per arm; fastest arm reported (%s)" % (args.cpu_frames, name),
+                               "arms": arms}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

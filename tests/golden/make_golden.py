@@ -60,3 +60,21 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_train_golden():
+    """train_case1.npz: the reference's training fixture (test.cpp:36-51 train_test: train_{rgb,dep,mask}.png
+    -> Detector().addTemplate -> writeClasses/06_template.yaml, the reference's own recorded output)."""
+    bk = importlib.import_module("6dpose_b200.bank")
+    rgb = cv2.imread(CASE + "train_rgb.png")
+    dep = cv2.imread(CASE + "train_dep.png", cv2.IMREAD_UNCHANGED)
+    mask = cv2.cvtColor(cv2.imread(CASE + "train_mask.png"), cv2.COLOR_RGB2GRAY)
+    ref = bk.TemplateBank()
+    ref.read_class(CASE + "writeClasses/06_template.yaml", 2)
+    p = ref.pack(["06_template"], 4)
+    np.savez_compressed(os.path.join(OUT, "train_case1.npz"), rgb=rgb, dep=dep, mask=mask, tmeta=p["tmeta"],
+                        feats=p["feats"].astype(np.int16))
+
+
+if __name__ == "__main__":
+    make_train_golden()
