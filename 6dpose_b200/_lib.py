@@ -237,9 +237,9 @@ class NativeDetector:
         return out
 
     def counters(self):
-        a = (ctypes.c_int64 * 5)()
+        a = (ctypes.c_int64 * 6)()
         check(self._L.lm_counters(self._h, a))
-        keys = ["templates", "coarse_candidates", "scan_bytes", "refine_bytes", "kept"]
+        keys = ["templates", "coarse_candidates", "scan_bytes", "refine_bytes", "kept", "refine_bytes_read"]
         return dict(zip(keys, [int(v) for v in a]))
 
     def set_timing(self, slots):

@@ -610,17 +610,22 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
   }
   if (!refine_only) {
     if (d->timing) CU(cudaEventRecord(d->ev[0], st));
-    // K1
-    for (int l = 0; l < d->L; ++l) {
-      const LevelHost& lv = d->lv[l];
+    // K1: one launch for every level and modality
+    {
       LinMemParams p;
-      for (int m = 0; m < d->M; ++m) p.q[m] = lv.q_src[m];
-      p.lm = lv.d_lm; p.T = lv.T; p.rows = lv.rows; p.cols = lv.cols; p.Wd = lv.Wd; p.Hd = lv.Hd; p.plane = lv.plane;
-      p.mod_stride = lv.mod_stride;
-      p.bp = lv.d_bp; p.lbw = lv.lbw;
-      const int n = lv.T * lv.T * lv.plane;
-      dim3 grid((unsigned)std::min((n + 255) / 256, d->sm_count * 8), (unsigned)d->M);
-      k_linear_memories<<<grid, 256, 0, st>>>(p);
+      p.L = d->L; p.M = d->M;
+      int blocks = 0;
+      for (int l = 0; l < d->L; ++l) {
+        const LevelHost& lv = d->lv[l];
+        LinMemLevel& q = p.lv[l];
+        for (int m = 0; m < d->M; ++m) q.q[m] = lv.q_src[m];
+        q.lm = lv.d_lm; q.bp = lv.d_bp; q.lbw = lv.lbw;
+        q.T = lv.T; q.rows = lv.rows; q.cols = lv.cols; q.Wd = lv.Wd; q.Hd = lv.Hd; q.plane = lv.plane;
+        q.mod_stride = lv.mod_stride;
+        blocks += (lv.T * lv.T * lv.plane + 255) / 256;
+        q.block_end = blocks;
+      }
+      k_linear_memories<<<dim3((unsigned)blocks, (unsigned)d->M), 256, 0, st>>>(p);
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[1], st));
@@ -905,7 +910,7 @@ extern "C" int lm_debug_linear_memories(lm_detector* d, int level, int modality,
   return LM_OK;
 }
 
-extern "C" int lm_counters(lm_detector* d, int64_t* out5) {
+extern "C" int lm_counters(lm_detector* d, int64_t* out5) {  // 6 entries
   if (!d || !out5) return fail(LM_E_INVALID, "null argument");
   if (!d->have_run) return fail(LM_E_STATE, "lm_run has not been called");
   out5[0] = d->shard_count;
@@ -913,6 +918,7 @@ extern "C" int lm_counters(lm_detector* d, int64_t* out5) {
   out5[2] = d->alg_scan_bytes;
   out5[3] = (int64_t)d->h_counters[0] * 256;
   out5[4] = d->h_res->count;
+  out5[5] = (int64_t)d->h_counters[1] * 256;
   return LM_OK;
 }
 

@@ -43,6 +43,17 @@ __device__ __forceinline__ int lm_min_passing_raw(float threshold, int nfeat) {
   return lo;
 }
 
+// Smallest raw score that survives remove_if(similarity < threshold) (LL.cpp:1935-1937); 4*nfeat + 1
+// when nothing can.
+__device__ __forceinline__ int lm_min_kept_raw(float threshold, int nfeat) {
+  int lo = 0, hi = 4 * nfeat + 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (!(lm_score(mid, nfeat) < threshold)) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
 // response of orientation o against spread mask v: the active SIMILARITY_LUT (LL.cpp:1121) is
 // 4 if bit o is set, else 1 if a neighbouring orientation bit is set, else 0 (checked against the
 // table in tests/test_oracle_cpu.py).
@@ -56,42 +67,74 @@ __device__ __forceinline__ uint32_t lm_response(uint32_t v, int o) {
 // K1: spread (OR over the forward TxT window) -> response maps -> linear memories
 //     (+ for the lowest level: the same spread masks as bit-planes, one bit per position and label)
 // --------------------------------------------------------------------------------------------
-struct LinMemParams {
+struct LinMemLevel {
   const uint8_t* q[LM_MAX_MODALITIES];  // quantized u8 rows x cols
   uint8_t* lm;
   uint32_t* bp;  // optional: [M][8][lbw] words, bit (grid*plane + pos) of block (m, o) = spread bit o
   int lbw;
   int T, rows, cols, Wd, Hd, plane;
   uint32_t mod_stride;
+  int block_end;  // blocks [previous end, block_end) of the launch belong to this level (per modality)
 };
 
+struct LinMemParams {
+  LinMemLevel lv[LM_MAX_LEVELS];
+  int L, M;
+};
+
+// OR of the forward TxT window at (x, y), clipped at the bottom/right image edge (LL.cpp:1094-1109).
+template <int T>
+__device__ __forceinline__ uint32_t spread_window(const uint8_t* __restrict__ q, int cols, int rows, int x, int y, int Trt) {
+  uint32_t v = 0;
+  const uint8_t* __restrict__ p0 = q + (size_t)y * cols + x;
+  if (T > 0 && x + T <= cols && y + T <= rows) {
+    // interior: T*T independent loads, fully unrolled (the dependent OR chain comes after the loads)
+    uint32_t t[T > 0 ? T * T : 1];
+#pragma unroll
+    for (int dy = 0; dy < T; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < T; ++dx) t[dy * T + dx] = __ldg(p0 + dy * cols + dx);
+#pragma unroll
+    for (int k = 0; k < T * T; ++k) v |= t[k];
+    return v;
+  }
+  const int y1 = min(y + Trt, rows), x1 = min(x + Trt, cols);
+  for (int yy = y; yy < y1; ++yy)
+    for (int xx = x; xx < x1; ++xx) v |= __ldg(q + (size_t)yy * cols + xx);
+  return v;
+}
+
 __global__ void __launch_bounds__(256) k_linear_memories(LinMemParams p) {
+  // which level does this block serve (<= 4 levels: linear search over the uniform block index)
+  int l = 0, first = 0;
+  while (l + 1 < p.L && (int)blockIdx.x >= p.lv[l].block_end) { first = p.lv[l].block_end; ++l; }
+  const LinMemLevel& lv = p.lv[l];
   const int m = blockIdx.y;
-  const int n = p.T * p.T * p.plane;
-  const uint8_t* __restrict__ q = (m == 0) ? p.q[0] : p.q[1];
-  uint8_t* __restrict__ out = p.lm + (size_t)m * p.mod_stride;
-  const int n_up = (n + 255) & ~255;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_up; i += gridDim.x * blockDim.x) {
-    uint32_t v = 0;
-    if (i < n) {
-      const int g = i / p.plane, pos = i - g * p.plane;
-      const int gy = g / p.T, gx = g - gy * p.T;
-      const int py = pos / p.Wd, px = pos - py * p.Wd;
-      const int y = py * p.T + gy, x = px * p.T + gx;
-      const int y1 = min(y + p.T, p.rows), x1 = min(x + p.T, p.cols);
-      for (int yy = y; yy < y1; ++yy) {
-        const uint8_t* row = q + (size_t)yy * p.cols;
-        for (int xx = x; xx < x1; ++xx) v |= __ldg(row + xx);
-      }
-#pragma unroll
-      for (int o = 0; o < 8; ++o) out[(size_t)o * n + i] = (uint8_t)lm_response(v, o);
+  const int n = lv.T * lv.T * lv.plane;
+  const uint8_t* __restrict__ q = (m == 0) ? lv.q[0] : lv.q[1];
+  uint8_t* __restrict__ out = lv.lm + (size_t)m * lv.mod_stride;
+  const int i = ((int)blockIdx.x - first) * 256 + (int)threadIdx.x;  // 32-aligned across a warp
+  uint32_t v = 0;
+  if (i < n) {
+    const int g = i / lv.plane, pos = i - g * lv.plane;
+    const int gy = g / lv.T, gx = g - gy * lv.T;
+    const int py = pos / lv.Wd, px = pos - py * lv.Wd;
+    const int y = py * lv.T + gy, x = px * lv.T + gx;
+    switch (lv.T) {
+      case 2: v = spread_window<2>(q, lv.cols, lv.rows, x, y, 2); break;
+      case 4: v = spread_window<4>(q, lv.cols, lv.rows, x, y, 4); break;
+      case 5: v = spread_window<5>(q, lv.cols, lv.rows, x, y, 5); break;
+      case 8: v = spread_window<8>(q, lv.cols, lv.rows, x, y, 8); break;
+      default: v = spread_window<0>(q, lv.cols, lv.rows, x, y, lv.T); break;
     }
-    if (p.bp) {  // warp-uniform; i is 32-aligned across the warp
 #pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        const uint32_t b = __ballot_sync(0xffffffffu, (v >> o) & 1u);
-        if ((threadIdx.x & 31) == 0 && i < n) p.bp[(size_t)(m * 8 + o) * p.lbw + (i >> 5)] = b;
-      }
+    for (int o = 0; o < 8; ++o) out[(size_t)o * n + i] = (uint8_t)lm_response(v, o);
+  }
+  if (lv.bp) {  // block-uniform
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const uint32_t b = __ballot_sync(0xffffffffu, (v >> o) & 1u);
+      if ((threadIdx.x & 31) == 0 && i < n) lv.bp[(size_t)(m * 8 + o) * lv.lbw + (i >> 5)] = b;
     }
   }
 }
@@ -181,63 +224,12 @@ __device__ __forceinline__ void vc_add8(uint32_t (&c)[8], const uint32_t (&x)[8]
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int R, bool kSmem>
-__global__ void __launch_bounds__(512, 1) k_coarse_bits(BitScanParams p) {
-  extern __shared__ __align__(128) uint32_t s_bp[];
-  __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ int s_next;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  // this CTA's slice of the work items; warps pull from it dynamically
-  const int t0 = (int)(((long long)p.n_items * blockIdx.x) / gridDim.x);
-  const int t1 = (int)(((long long)p.n_items * (blockIdx.x + 1)) / gridDim.x);
-  if (threadIdx.x == 0) s_next = t0 + nwarps;
-
-  const uint32_t* __restrict__ bp = p.bp;
-  if (kSmem) {
-    // one elected thread stages every bit-plane with bulk async copies (TMA, 1-D) onto an mbarrier
-    const uint32_t bar = smem_u32(&s_bar);
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const uint32_t bytes = p.bp_words * 4u;  // multiple of 16 (lbw is a multiple of 4)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      const char* src = reinterpret_cast<const char*>(p.bp);
-      uint32_t dst = smem_u32(s_bp);
-      for (uint32_t done = 0; done < bytes;) {
-        const uint32_t n = min(bytes - done, 32768u);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + done),
-                     "l"(src + done), "r"(n), "r"(bar)
-                     : "memory");
-        done += n;
-      }
-    }
-    // everyone waits for phase 0 of the barrier
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar)
-        : "memory");
-    bp = s_bp;
-  } else {
-    __syncthreads();
-  }
-
-  int it = t0 + warp;
-  while (it < t1) {
-    const int w = p.items[it];
-    const int g = p.work[w];
-    int nfeat = 0;
-    for (int m = 0; m < p.M; ++m) nfeat += p.tslot[(size_t)g * p.S + p.slot_low + m].y;
-    const int P = p.tslot[(size_t)g * p.S + p.slot_low].z;  // equal for all modalities (host checked)
-
+// One template, RR rounds of 32 position words (RR <= the level's rounds: positions at or beyond
+// template_positions P are zero by definition, so templates with P <= 1024 * RR need no more).
+template <int RR>
+__device__ __forceinline__ int coarse_bits_template(const BitScanParams& p, const uint32_t* __restrict__ bp, int lane, int w, int g,
+                                                    int nfeat, int P) {
+  constexpr int R = RR;
     uint32_t ch[R][8], cn[R][8];
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -333,6 +325,84 @@ __global__ void __launch_bounds__(512, 1) k_coarse_bits(BitScanParams p) {
         }
       }
     }
+    // words beyond the rounds computed: every position is >= P, i.e. raw 0 (passes only if 0 does)
+    for (int idx = lane + 32 * R; idx < p.nwords; idx += 32) {
+      const int j0 = idx * 32;
+      uint32_t pass = 0u;
+      if (raw_min == 0) {
+        pass = (p.plane - j0 < 32) ? (0xffffffffu >> (32 - (p.plane - j0))) : 0xffffffffu;
+        for (int b = 0; b < 32; ++b)
+          if ((pass >> b) & 1u) p.raw[(size_t)w * p.plane + j0 + b] = 0;
+      }
+      p.mask[(size_t)w * p.nwords + idx] = pass;
+      my_count += __popc(pass);
+    }
+    return my_count;
+}
+
+template <int R, bool kSmem>
+__global__ void __launch_bounds__(512, 1) k_coarse_bits(BitScanParams p) {
+  extern __shared__ __align__(128) uint32_t s_bp[];
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_next;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // this CTA's slice of the work items; warps pull from it dynamically
+  const int t0 = (int)(((long long)p.n_items * blockIdx.x) / gridDim.x);
+  const int t1 = (int)(((long long)p.n_items * (blockIdx.x + 1)) / gridDim.x);
+  if (threadIdx.x == 0) s_next = t0 + nwarps;
+
+  const uint32_t* __restrict__ bp = p.bp;
+  if (kSmem) {
+    // one elected thread stages every bit-plane with bulk async copies (TMA, 1-D) onto an mbarrier
+    const uint32_t bar = smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = p.bp_words * 4u;  // multiple of 16 (lbw is a multiple of 4)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      const char* src = reinterpret_cast<const char*>(p.bp);
+      uint32_t dst = smem_u32(s_bp);
+      for (uint32_t done = 0; done < bytes;) {
+        const uint32_t n = min(bytes - done, 32768u);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + done),
+                     "l"(src + done), "r"(n), "r"(bar)
+                     : "memory");
+        done += n;
+      }
+    }
+    // everyone waits for phase 0 of the barrier
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar)
+        : "memory");
+    bp = s_bp;
+  } else {
+    __syncthreads();
+  }
+
+  int it = t0 + warp;
+  while (it < t1) {
+    const int w = p.items[it];
+    const int g = p.work[w];
+    int nfeat = 0;
+    for (int m = 0; m < p.M; ++m) nfeat += p.tslot[(size_t)g * p.S + p.slot_low + m].y;
+    const int P = p.tslot[(size_t)g * p.S + p.slot_low].z;  // equal for all modalities (host checked)
+    const int need = max(1, (((P + 31) >> 5) + 31) >> 5);    // rounds that hold positions < P
+    int my_count;
+    if (R >= 2 && need == 1) my_count = coarse_bits_template<1>(p, bp, lane, w, g, nfeat, P);
+    else if (R >= 3 && need == 2) my_count = coarse_bits_template<(R >= 3 ? 2 : 1)>(p, bp, lane, w, g, nfeat, P);
+    else if (R >= 4 && need == 3) my_count = coarse_bits_template<(R >= 4 ? 3 : 1)>(p, bp, lane, w, g, nfeat, P);
+    else if (R >= 5 && need == 4) my_count = coarse_bits_template<(R >= 5 ? 4 : 1)>(p, bp, lane, w, g, nfeat, P);
+    else my_count = coarse_bits_template<R>(p, bp, lane, w, g, nfeat, P);
     my_count = __reduce_add_sync(0xffffffffu, my_count);
     if (lane == 0) p.cnt[w] = my_count;
 
@@ -485,7 +555,8 @@ struct RefineParams {
   float threshold;
   lm_result_header* hdr;  // result block: header, then `capacity` records
   int32_t capacity;
-  unsigned long long* counters;  // [0] refinement feature-rows processed (x256 = bytes)
+  unsigned long long* counters;  // [0] features x candidates of the reference's refinement (x256 = algorithmic
+                                 // bytes), [1] features actually read (early exit)
   const uint8_t* safe;           // per template: no feature can leave the image once a clamped patch
                                  // offset is applied (LL.cpp:1394 never skips) -> 128-bit row loads
   const uint16_t* galign;        // [G][S][16]: features per (fbase & 15) group (refined levels are stored
@@ -530,7 +601,7 @@ __global__ void __launch_bounds__(256, 3) k_refine(RefineParams p) {
   const int total = p.off[p.n_work];
   const LevelDev low = p.lv[p.L - 1];
   const int row = lane >> 1, half = lane & 1;
-  unsigned long long feats_done = 0;
+  unsigned long long feats_done = 0, feats_read = 0;
   lm_record* __restrict__ out = reinterpret_cast<lm_record*>(p.hdr + 1);
 
   for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < total; c += nwarps) {
@@ -593,6 +664,7 @@ __global__ void __launch_bounds__(256, 3) k_refine(RefineParams p) {
 
       uint32_t s01 = 0, s23 = 0, s45 = 0, s67 = 0;
       int nf2 = 0;
+      bool pruned = false;
       if (p.safe[g] && (lv.Wd & 15) == 0) {
         // Fast path.  Every row of the 16x16 patch starts at the same offset inside its 16-byte
         // chunk (Wd is a multiple of 16), so the two lanes of a row fetch the two aligned chunks that
@@ -601,14 +673,22 @@ __global__ void __launch_bounds__(256, 3) k_refine(RefineParams p) {
         // row start (which decides who trades what) is constant over a whole group of features.
         const uint4* __restrict__ lm128 = reinterpret_cast<const uint4*>(lv.lm);
         const uint32_t shift_row = (uint32_t)(cy * lv.Wd + cx + row * lv.Wd);
-        for (int m = 0; m < p.M; ++m) {
+        // Early exit (exact): a candidate only produces output if its best cell reaches raw_keep.  Every
+        // remaining feature adds at most 4 to any cell, so once max(cells so far) + 4 * remaining falls
+        // short the candidate is dropped (LL.cpp:1935-1937) whatever the rest adds -- stop reading.
+        int nf_level = 0;
+        for (int m = 0; m < p.M; ++m) nf_level += p.tslot[(size_t)g * p.S + l * p.M + m].y;
+        const int raw_keep = lm_min_kept_raw(p.threshold, nf_level);
+        int done = 0;
+        feats_done += nf_level;  // the reference's work for this candidate (algorithmic bytes / 256)
+        for (int m = 0; m < p.M && !pruned; ++m) {
           const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
           nf2 += ts.y;
           const uint32_t* __restrict__ fb = p.fbase + ts.x;
           const uint16_t* __restrict__ ga = p.galign + ((size_t)g * p.S + l * p.M + m) * 16;
           uint32_t a8 = 0, b8 = 0;
           int pend = 0;
-          for (int grp = 0; grp < 16; ++grp) {
+          for (int grp = 0; grp < 16 && !pruned; ++grp) {
             int n = ga[grp];
             const uint32_t o = ((uint32_t)grp + shift_row) & 15u;
             const uint32_t sh = (o & 3u) << 3;
@@ -623,18 +703,24 @@ __global__ void __launch_bounds__(256, 3) k_refine(RefineParams p) {
               fb += take;
               n -= take;
               pend += take;
+              done += take;
               if (pend == 63) {  // 63 * 4 = 252: no carry between packed bytes
                 s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
                 s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
                 a8 = b8 = 0;
                 pend = 0;
+                uint32_t mx = max(max(max(s01 & 0xFFFF, s01 >> 16), max(s23 & 0xFFFF, s23 >> 16)),
+                                  max(max(s45 & 0xFFFF, s45 >> 16), max(s67 & 0xFFFF, s67 >> 16)));
+                mx = __reduce_max_sync(0xffffffffu, mx);
+                if ((int)mx + 4 * (nf_level - done) < raw_keep) { pruned = true; break; }
               }
             }
           }
           s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
           s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
-          feats_done += ts.y;
         }
+        feats_read += done;
+        nf2 = nf_level;
       } else
       for (int m = 0; m < p.M; ++m) {
         const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
@@ -653,6 +739,7 @@ __global__ void __launch_bounds__(256, 3) k_refine(RefineParams p) {
           a8 += __funnelshift_r(w0, w1, sh);
           b8 += __funnelshift_r(w1, w2, sh);
           ++feats_done;
+          ++feats_read;
           if (++pend == 63) {
             s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
             s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
@@ -681,7 +768,7 @@ __global__ void __launch_bounds__(256, 3) k_refine(RefineParams p) {
       sim = lm_score(best_raw, nf2);
       x = (x / T - 8 + bc) * T + lv.off;  // LL.cpp:1930-1931
       y = (y / T - 8 + br) * T + lv.off;
-      kept = !(sim < p.threshold);  // remove_if(similarity < threshold), LL.cpp:1935-1937
+      kept = !pruned && !(sim < p.threshold);  // remove_if(similarity < threshold), LL.cpp:1935-1937
     }
     if (lane == 0 && kept) {
       // unordered append; (work, seq) restores the reference's pre-sort order on the host
@@ -695,5 +782,8 @@ __global__ void __launch_bounds__(256, 3) k_refine(RefineParams p) {
       }
     }
   }
-  if (lane == 0 && feats_done) atomicAdd(p.counters + 0, feats_done);
+  if (lane == 0 && feats_done) {
+    atomicAdd(p.counters + 0, feats_done);
+    atomicAdd(p.counters + 1, feats_read);
+  }
 }

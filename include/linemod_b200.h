@@ -132,8 +132,10 @@ int lm_debug_linear_memories(lm_detector* d, int level, int modality, uint8_t* o
 /* Counters of the last lm_run: [0] templates scanned, [1] coarse candidates, [2] algorithmic bytes of
  * the coarse scan (sum over templates, modalities of features x positions),
  * [3] algorithmic bytes of the refinement (features x 256 per refined candidate and level),
- * [4] records kept after refinement.  [0],[2] describe this handle's shard. */
-int lm_counters(lm_detector* d, int64_t* out5);
+ * [4] records kept after refinement, [5] bytes the refinement kernel actually read (it stops early,
+ * exactly, on candidates that can no longer reach the threshold).  [0],[2] describe this handle's
+ * shard.  `out6` has 6 entries. */
+int lm_counters(lm_detector* d, int64_t* out6);
 /* Per-stage device time in microseconds, from CUDA events recorded on the detector's stream around
  * each stage: [0] linear memories, [1] coarse scan, [2] candidate offsets, [3] refinement, [4] total.
  * lm_set_timing(d, slots) with slots > 0 enables it and keeps the last `slots` runs (0 disables);
