@@ -595,7 +595,7 @@ __device__ __forceinline__ void refine_rows(const uint4* __restrict__ lm128, con
   }
 }
 
-__global__ void __launch_bounds__(256, 3) k_refine(RefineParams p) {
+__global__ void __launch_bounds__(256, 4) k_refine(RefineParams p) {
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int total = p.off[p.n_work];
