@@ -168,7 +168,7 @@ def run_reference(args):
                          "arms": arms},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
 
 
 def workload_config(args, n):
@@ -181,7 +181,20 @@ def workload_config(args, n):
                   "L2-resident by design" % (args.ring, args.ring * (args.width * args.height * 2 * 1.25) / 1e6)}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The driver expects exactly ONE line on stdout: the JSON.  Libraries (NCCL prints its version
+    banner to stdout) are kept away from it by pointing fd 1 at stderr for the whole run."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
@@ -274,7 +287,8 @@ def main():
     barrier()
 
     # ---- e2e: host buffers through the C-ABI match call ------------------------------------------
-    nat.set_result_buffer(0, 0)
+    if world == 1:
+        nat.set_result_buffer(0, 0)
     host_frames = []
     for q in frames[:min(len(frames), 64)]:
         hq = [[torch.from_numpy(np.ascontiguousarray(q[l][m])).pin_memory().numpy() for m in range(2)] for l in range(2)]
@@ -286,13 +300,17 @@ def main():
         if world == 1:
             return nat.match_quantized(q, args.threshold)
         nat.upload_quantized(q)
-        nat.run(args.threshold)
-        rec = nat.fetch_records()
-        allrec = [None] * world
-        dist.all_gather_object(allrec, rec)
-        if rank == 0:
-            return nat.finish(np.concatenate(allrec))
-        return rec
+        nat.enqueue(args.threshold)
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(gathered, res)   # fixed-size result blocks, one NCCL all-gather
+            host = gathered.to("cpu", non_blocking=False)
+        nat.complete()
+        blocks = host.numpy().reshape(world, blk_bytes)
+        parts = []
+        for r in range(world):
+            n = int(blocks[r, :4].view(np.int32)[0])
+            parts.append(blocks[r, 16:16 + 16 * n].view(lib.RECORD_DTYPE))
+        return nat.finish(np.concatenate(parts))
 
     for i in range(3):
         out = e2e_step(i)
@@ -359,7 +377,7 @@ def main():
         out["cpu_baseline"] = {"value": arms[name]["fps"], "unit": "frames/s", "cores": arms[name]["cores"], "kind": kind,
                                "sample": "%d full frames of the same workload per arm; fastest arm reported (%s)" % (args.cpu_frames, name),
                                "arms": arms}
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
 
