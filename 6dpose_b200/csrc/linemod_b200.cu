@@ -614,6 +614,19 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     {
       LinMemParams p;
       p.L = d->L; p.M = d->M;
+      bool band = true;
+      size_t smem = 0;
+      for (int l = 0; l < d->L; ++l) {
+        const LevelHost& lv = d->lv[l];
+        band = band && (lv.cols % 4 == 0) && (lv.Wd % 4 == 0) && (lv.plane % 4 == 0);
+        // column segments: as many as keep a multiple of 4 positions per segment (more CTAs in flight)
+        int nseg = 1;
+        while (nseg < 8 && lv.Wd % (nseg * 2 * 4) == 0 && (lv.T * lv.T * lv.Wd) / (nseg * 2 * 4) >= 128) nseg *= 2;
+        p.lv[l].nseg = nseg;
+        const size_t wp = (size_t)((lv.Wd / nseg * lv.T + lv.T + 3 + 4) & ~3);
+        smem = std::max(smem, wp * (size_t)(2 * (2 * lv.T - 1) + lv.T));
+      }
+      band = band && smem <= 160 * 1024;
       int blocks = 0;
       for (int l = 0; l < d->L; ++l) {
         const LevelHost& lv = d->lv[l];
@@ -622,10 +635,21 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
         q.lm = lv.d_lm; q.bp = lv.d_bp; q.lbw = lv.lbw;
         q.T = lv.T; q.rows = lv.rows; q.cols = lv.cols; q.Wd = lv.Wd; q.Hd = lv.Hd; q.plane = lv.plane;
         q.mod_stride = lv.mod_stride;
-        blocks += (lv.T * lv.T * lv.plane + 255) / 256;
+        blocks += band ? lv.Hd * q.nseg : (lv.T * lv.T * lv.plane + 255) / 256;
         q.block_end = blocks;
       }
-      k_linear_memories<<<dim3((unsigned)blocks, (unsigned)d->M), 256, 0, st>>>(p);
+      if (band) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          CU(cudaFuncSetAttribute(k_linear_memories_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+          attr_set = true;
+        }
+        const LevelHost& low = d->lv[d->L - 1];
+        (void)low;  // bit-planes are OR-ed in: zero at allocation, re-zeroed by k_refine after every frame
+        k_linear_memories_band<<<dim3((unsigned)blocks, (unsigned)d->M), 128, smem, st>>>(p);
+      } else {
+        k_linear_memories<<<dim3((unsigned)blocks, (unsigned)d->M), 256, 0, st>>>(p);
+      }
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[1], st));
@@ -667,12 +691,14 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[2], st));
-    k_scan_counts<<<1, 1024, 0, st>>>(d->d_cnt, d->d_off, n_work, d->d_res, (int)d->res_cap, d->shard_index);
+    k_scan_counts<<<1, 1024, 0, st>>>(d->d_cnt, d->d_off, n_work, d->d_res, (int)d->res_cap, d->shard_index, d->d_counters);
     ++d->launches;
     if (d->timing) CU(cudaEventRecord(d->ev[3], st));
   }
-  CU(cudaMemsetAsync(d->d_counters, 0, 2 * sizeof(unsigned long long), st));
-  if (refine_only) CU(cudaMemsetAsync(&d->d_res->count, 0, sizeof(int32_t), st));
+  if (refine_only) {
+    CU(cudaMemsetAsync(d->d_counters, 0, 2 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(&d->d_res->count, 0, sizeof(int32_t), st));
+  }
   {
     // persistent grid: the candidate total is read on the device (no host round trip)
     RefineParams rp;
@@ -685,6 +711,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     rp.hdr = d->d_res; rp.capacity = (int32_t)d->res_cap;
     rp.counters = d->d_counters;
     rp.safe = d->d_safe; rp.galign = d->d_galign;
+    rp.bp_clear = low.d_bp; rp.bp_words = low.d_bp ? (uint32_t)((size_t)d->M * 8 * low.lbw) : 0u;
     k_refine<<<d->sm_count * 8, 256, 0, st>>>(rp);
     ++d->launches;
   }

@@ -75,6 +75,7 @@ struct LinMemLevel {
   int T, rows, cols, Wd, Hd, plane;
   uint32_t mod_stride;
   int block_end;  // blocks [previous end, block_end) of the launch belong to this level (per modality)
+  int nseg;       // band kernel: column segments per row of positions (Wd / nseg is a multiple of 4)
 };
 
 struct LinMemParams {
@@ -135,6 +136,83 @@ __global__ void __launch_bounds__(256) k_linear_memories(LinMemParams p) {
     for (int o = 0; o < 8; ++o) {
       const uint32_t b = __ballot_sync(0xffffffffu, (v >> o) & 1u);
       if ((threadIdx.x & 31) == 0 && i < n) lv.bp[(size_t)(m * 8 + o) * lv.lbw + (i >> 5)] = b;
+    }
+  }
+}
+
+// K1 (band version): one CTA per (level, modality, row of sampled positions).  The band of T image rows
+// (+ T-1 rows below for the forward window) is staged in shared memory, the TxT OR is done separably
+// (horizontal then vertical, 4 pixels per 32-bit op), and the responses of 4 consecutive positions of
+// one (label, grid) plane are computed SIMD-in-register and written with one 32-bit store.  Needs
+// cols % 4 == 0 and Wd % 4 == 0 (every BASELINE size); other sizes use k_linear_memories above.
+// Bit-planes are OR-ed in with atomics (the caller zeroes them first).
+__global__ void __launch_bounds__(256) k_linear_memories_band(LinMemParams p) {
+  extern __shared__ __align__(16) uint8_t s_band[];
+  int l = 0, first = 0;
+  while (l + 1 < p.L && (int)blockIdx.x >= p.lv[l].block_end) { first = p.lv[l].block_end; ++l; }
+  const LinMemLevel& lv = p.lv[l];
+  const int m = blockIdx.y;
+  const int bi = (int)blockIdx.x - first;
+  const int py = bi / lv.nseg, seg = bi - py * lv.nseg;  // row of sampled positions, column segment
+  const int T = lv.T, cols = lv.cols, rows = lv.rows, Wd = lv.Wd;
+  const int Wseg = Wd / lv.nseg;        // positions in this segment (multiple of 4)
+  const int x0 = seg * Wseg * T;        // first image column of the segment
+  const int cseg = Wseg * T;            // image columns that produce this segment's positions
+  const int Wp = (cseg + T + 3 + 4) & ~3;  // padded row pitch: the forward window needs T-1 more columns
+  const int nin = 2 * T - 1;
+  uint8_t* s_in = s_band;               // [nin][Wp]
+  uint8_t* s_h = s_in + nin * Wp;       // [nin][Wp] horizontal OR
+  uint8_t* s_sp = s_h + nin * Wp;       // [T][Wp]   spread mask of the band
+  const uint8_t* __restrict__ q = (m == 0) ? lv.q[0] : lv.q[1];
+  const int y0 = py * T;
+  const int wpr = Wp >> 2, cw = cseg >> 2;
+  // A: stage the input rows (zero beyond the image = clipping at the bottom/right edge)
+  for (int i = threadIdx.x; i < nin * wpr; i += blockDim.x) {
+    const int r = i / wpr, w = i - r * wpr;
+    uint32_t v = 0;
+    if (x0 + 4 * w < cols && y0 + r < rows) v = __ldg(reinterpret_cast<const uint32_t*>(q + (size_t)(y0 + r) * cols + x0) + w);
+    reinterpret_cast<uint32_t*>(s_in)[i] = v;
+  }
+  __syncthreads();
+  // B: horizontal OR over dx < T, 4 pixels at a time
+  for (int i = threadIdx.x; i < nin * cw; i += blockDim.x) {
+    const int r = i / cw, w = i - r * cw;
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(s_in + r * Wp);
+    uint32_t acc = 0;
+    for (int dx = 0; dx < T; ++dx) {
+      const int b = 4 * w + dx;
+      acc |= __funnelshift_r(row[b >> 2], row[(b >> 2) + 1], (b & 3) << 3);
+    }
+    reinterpret_cast<uint32_t*>(s_h + r * Wp)[w] = acc;
+  }
+  __syncthreads();
+  // C: vertical OR over dy < T
+  for (int i = threadIdx.x; i < T * cw; i += blockDim.x) {
+    const int r = i / cw, w = i - r * cw;
+    uint32_t acc = 0;
+    for (int dy = 0; dy < T; ++dy) acc |= reinterpret_cast<const uint32_t*>(s_h + (r + dy) * Wp)[w];
+    reinterpret_cast<uint32_t*>(s_sp + r * Wp)[w] = acc;
+  }
+  __syncthreads();
+  // D: responses in linear-memory order, 4 positions per store
+  const int T2 = T * T, q4 = Wseg >> 2;
+  const int n = T2 * lv.plane;
+  uint8_t* __restrict__ out = lv.lm + (size_t)m * lv.mod_stride;
+  for (int i = threadIdx.x; i < T2 * q4; i += blockDim.x) {
+    const int g = i / q4, k = i - g * q4;
+    const int gy = g / T, gx = g - gy * T;
+    const uint8_t* sp = s_sp + gy * Wp + (4 * k) * T + gx;
+    const uint32_t V = (uint32_t)sp[0] | ((uint32_t)sp[T] << 8) | ((uint32_t)sp[2 * T] << 16) | ((uint32_t)sp[3 * T] << 24);
+    const int pos = g * lv.plane + py * Wd + seg * Wseg + 4 * k;  // multiple of 4
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const uint32_t hit = (V >> o) & 0x01010101u;
+      const uint32_t nb = ((V >> ((o + 1) & 7)) | (V >> ((o + 7) & 7))) & 0x01010101u;
+      *reinterpret_cast<uint32_t*>(out + (size_t)o * n + pos) = (hit << 2) | (nb & ~hit);
+      if (lv.bp) {
+        const uint32_t nib = ((hit * 0x01020408u) >> 24) & 0xFu;  // the 4 hit bits, position order
+        if (nib) atomicOr(lv.bp + (size_t)(m * 8 + o) * lv.lbw + (pos >> 5), nib << (pos & 31));
+      }
     }
   }
 }
@@ -517,7 +595,8 @@ __global__ void __launch_bounds__(1024) k_coarse_bytes(ByteScanParams p) {
 // exclusive scan of the per-template candidate counts -> global candidate offsets (ordered)
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
-                                                     lm_result_header* __restrict__ hdr, int capacity, int shard) {
+                                                     lm_result_header* __restrict__ hdr, int capacity, int shard,
+                                                     unsigned long long* __restrict__ counters) {
   __shared__ int s_warp[33];
   const int per = (n + blockDim.x - 1) / blockDim.x;
   const int b = threadIdx.x * per, e = min(b + per, n);
@@ -535,6 +614,8 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
     hdr->coarse_candidates = total;
     hdr->capacity = capacity;
     hdr->shard = shard;
+    counters[0] = 0ull;  // k_refine accumulates into them
+    counters[1] = 0ull;
   }
 }
 
@@ -561,6 +642,8 @@ struct RefineParams {
                                  // offset is applied (LL.cpp:1394 never skips) -> 128-bit row loads
   const uint16_t* galign;        // [G][S][16]: features per (fbase & 15) group (refined levels are stored
                                  // grouped by it)
+  uint32_t* bp_clear;            // lowest level's bit-planes: consumed by the coarse scan of this frame,
+  uint32_t bp_words;             // cleared here for the next frame's K1 (which ORs its bits in)
 };
 
 // One lane pair = one row of the 16x16 patch: lane `half` loads the aligned 16-byte chunk (a >> 4) +
@@ -603,6 +686,8 @@ __global__ void __launch_bounds__(256, 4) k_refine(RefineParams p) {
   const int row = lane >> 1, half = lane & 1;
   unsigned long long feats_done = 0, feats_read = 0;
   lm_record* __restrict__ out = reinterpret_cast<lm_record*>(p.hdr + 1);
+  if (p.bp_clear)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.bp_words; i += gridDim.x * blockDim.x) p.bp_clear[i] = 0u;
 
   for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < total; c += nwarps) {
     // template of candidate c: last w with off[w] <= c
