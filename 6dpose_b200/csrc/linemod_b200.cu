@@ -583,6 +583,18 @@ static LevelDev level_dev(const LevelHost& h) {
   return v;
 }
 
+// Launch with programmatic stream serialization (see lm_pdl_wait in lm_kernels.cuh).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int R>
 static cudaError_t launch_coarse_bits(const BitScanParams& bp, bool smem, size_t smem_bytes, int grid, cudaStream_t st) {
   if (smem) {
@@ -592,11 +604,9 @@ static cudaError_t launch_coarse_bits(const BitScanParams& bp, bool smem, size_t
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    k_coarse_bits<R, true><<<grid, 512, smem_bytes, st>>>(bp);
-  } else {
-    k_coarse_bits<R, false><<<grid, 512, 0, st>>>(bp);
+    return launch_pdl(k_coarse_bits<R, true>, dim3(grid), dim3(512), smem_bytes, st, bp);
   }
-  return cudaGetLastError();
+  return launch_pdl(k_coarse_bits<R, false>, dim3(grid), dim3(512), 0, st, bp);
 }
 
 // Enqueue every GPU stage of one frame on the detector's stream; no host synchronisation.
@@ -646,9 +656,9 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
         }
         const LevelHost& low = d->lv[d->L - 1];
         (void)low;  // bit-planes are OR-ed in: zero at allocation, re-zeroed by k_refine after every frame
-        k_linear_memories_band<<<dim3((unsigned)blocks, (unsigned)d->M), 128, smem, st>>>(p);
+        CU(launch_pdl(k_linear_memories_band, dim3((unsigned)blocks, (unsigned)d->M), dim3(128), smem, st, p));
       } else {
-        k_linear_memories<<<dim3((unsigned)blocks, (unsigned)d->M), 256, 0, st>>>(p);
+        CU(launch_pdl(k_linear_memories, dim3((unsigned)blocks, (unsigned)d->M), dim3(256), 0, st, p));
       }
       ++d->launches;
     }
@@ -687,11 +697,11 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       sp.mask = d->d_mask; sp.raw = d->d_raw; sp.cnt = d->d_cnt;
       int bs = ((low.plane + 3) / 4 + 31) / 32 * 32;
       bs = std::max(32, std::min(bs, 1024));
-      k_coarse_bytes<<<d->n_items_bytes, bs, 0, st>>>(sp);
+      CU(launch_pdl(k_coarse_bytes, dim3(d->n_items_bytes), dim3(bs), 0, st, sp));
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[2], st));
-    k_scan_counts<<<1, 1024, 0, st>>>(d->d_cnt, d->d_off, n_work, d->d_res, (int)d->res_cap, d->shard_index, d->d_counters);
+    CU(launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, (const int32_t*)d->d_cnt, d->d_off, n_work, d->d_res, (int)d->res_cap, d->shard_index, d->d_counters));
     ++d->launches;
     if (d->timing) CU(cudaEventRecord(d->ev[3], st));
   }
@@ -712,7 +722,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     rp.counters = d->d_counters;
     rp.safe = d->d_safe; rp.galign = d->d_galign;
     rp.bp_clear = low.d_bp; rp.bp_words = low.d_bp ? (uint32_t)((size_t)d->M * 8 * low.lbw) : 0u;
-    k_refine<<<d->sm_count * 8, 256, 0, st>>>(rp);
+    CU(launch_pdl(k_refine, dim3(d->sm_count * 8), dim3(256), 0, st, rp));
     ++d->launches;
   }
   if (d->timing) CU(cudaEventRecord(d->ev[4], st));

@@ -63,6 +63,11 @@ __device__ __forceinline__ uint32_t lm_response(uint32_t v, int o) {
   return hit ? 4u : nb;
 }
 
+// Programmatic dependent launch: every kernel of the per-frame chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its launch latency overlaps the tail of its
+// predecessor; it must not touch the predecessor's results before this wait returns.
+__device__ __forceinline__ void lm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // --------------------------------------------------------------------------------------------
 // K1: spread (OR over the forward TxT window) -> response maps -> linear memories
 //     (+ for the lowest level: the same spread masks as bit-planes, one bit per position and label)
@@ -106,6 +111,7 @@ __device__ __forceinline__ uint32_t spread_window(const uint8_t* __restrict__ q,
 }
 
 __global__ void __launch_bounds__(256) k_linear_memories(LinMemParams p) {
+  lm_pdl_wait();
   // which level does this block serve (<= 4 levels: linear search over the uniform block index)
   int l = 0, first = 0;
   while (l + 1 < p.L && (int)blockIdx.x >= p.lv[l].block_end) { first = p.lv[l].block_end; ++l; }
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(256) k_linear_memories(LinMemParams p) {
 // cols % 4 == 0 and Wd % 4 == 0 (every BASELINE size); other sizes use k_linear_memories above.
 // Bit-planes are OR-ed in with atomics (the caller zeroes them first).
 __global__ void __launch_bounds__(256) k_linear_memories_band(LinMemParams p) {
+  lm_pdl_wait();
   extern __shared__ __align__(16) uint8_t s_band[];
   int l = 0, first = 0;
   while (l + 1 < p.L && (int)blockIdx.x >= p.lv[l].block_end) { first = p.lv[l].block_end; ++l; }
@@ -420,6 +427,7 @@ __device__ __forceinline__ int coarse_bits_template(const BitScanParams& p, cons
 
 template <int R, bool kSmem>
 __global__ void __launch_bounds__(512, 1) k_coarse_bits(BitScanParams p) {
+  lm_pdl_wait();
   extern __shared__ __align__(128) uint32_t s_bp[];
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_next;
@@ -512,6 +520,7 @@ struct ByteScanParams {
 #define SCAN_FEAT_TILE 512
 
 __global__ void __launch_bounds__(1024) k_coarse_bytes(ByteScanParams p) {
+  lm_pdl_wait();
   __shared__ uint32_t s_base[SCAN_FEAT_TILE];
   __shared__ int s_count;
   const int w = p.items[blockIdx.x];
@@ -597,6 +606,7 @@ __global__ void __launch_bounds__(1024) k_coarse_bytes(ByteScanParams p) {
 __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
                                                      lm_result_header* __restrict__ hdr, int capacity, int shard,
                                                      unsigned long long* __restrict__ counters) {
+  lm_pdl_wait();
   __shared__ int s_warp[33];
   const int per = (n + blockDim.x - 1) / blockDim.x;
   const int b = threadIdx.x * per, e = min(b + per, n);
@@ -679,6 +689,7 @@ __device__ __forceinline__ void refine_rows(const uint4* __restrict__ lm128, con
 }
 
 __global__ void __launch_bounds__(256, 4) k_refine(RefineParams p) {
+  lm_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int total = p.off[p.n_work];
