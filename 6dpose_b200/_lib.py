@@ -20,7 +20,7 @@ HEADER_DTYPE = np.dtype([("count", "<i4"), ("coarse_candidates", "<i4"), ("capac
 # every symbol include/linemod_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "lm_last_error", "lm_create", "lm_destroy", "lm_load_bank", "lm_select", "lm_shard_range",
-    "lm_upload_quantized", "lm_bind_quantized_device", "lm_run", "lm_enqueue", "lm_complete", "lm_set_result_buffer", "lm_device_result", "lm_fetch_records",
+    "lm_upload_quantized", "lm_upload_images", "lm_match_images", "lm_debug_quantized", "lm_bind_quantized_device", "lm_run", "lm_enqueue", "lm_complete", "lm_set_result_buffer", "lm_device_result", "lm_fetch_records",
     "lm_finish", "lm_match_quantized", "lm_debug_linear_memories", "lm_counters", "lm_set_timing",
     "lm_stage_times", "lm_stream", "lm_launch_count",
     "lm_icp_create", "lm_icp_destroy", "lm_icp_process", "lm_icp_process_batch", "lm_icp_last_stats", "lm_icp_launch_count", "lm_icp_set_use_scene_cloud",
@@ -54,6 +54,11 @@ def load():
     L.lm_select.argtypes = [vp, i32p, c_int, c_int, c_int]
     L.lm_shard_range.argtypes = [vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
     L.lm_upload_quantized.argtypes = [vp, u8pp, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
+    u8p_ = ctypes.POINTER(ctypes.c_uint8)
+    L.lm_upload_images.argtypes = [vp, u8p_, ctypes.POINTER(ctypes.c_uint16), c_int, c_int, u8p_, u8p_]
+    L.lm_match_images.argtypes = [vp, u8p_, ctypes.POINTER(ctypes.c_uint16), c_int, c_int, u8p_, u8p_, c_f, vp, c_i64,
+                                  ctypes.POINTER(c_i64)]
+    L.lm_debug_quantized.argtypes = [vp, c_int, c_int, u8p_, c_i64]
     L.lm_bind_quantized_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
     L.lm_run.argtypes = [vp, c_f]
     L.lm_enqueue.argtypes = [vp, c_f]
@@ -170,6 +175,52 @@ class NativeDetector:
     def upload_quantized(self, quantized):
         qs, ptrs, r, c = self._frame_args(quantized)
         check(self._L.lm_upload_quantized(self._h, ptrs, r, c))
+
+    @staticmethod
+    def _image_args(rgb, depth, masks):
+        rgb = np.ascontiguousarray(rgb)
+        depth = np.ascontiguousarray(depth)
+        if rgb.dtype != np.uint8 or rgb.ndim != 3 or rgb.shape[2] != 3:
+            raise TypeError("sources[0] must be a uint8 HxWx3 colour image")
+        if depth.dtype != np.uint16 or depth.shape != rgb.shape[:2]:
+            raise TypeError("sources[1] must be a uint16 HxW depth image of the same size")
+        mk = [None, None]
+        if masks:
+            if len(masks) != 2:
+                raise RuntimeError("masks.size() == modalities.size()")
+            for i, m in enumerate(masks):
+                if m is not None and np.asarray(m).size:
+                    m = np.ascontiguousarray(m)
+                    if m.dtype != np.uint8 or m.shape != rgb.shape[:2]:
+                        raise RuntimeError("mask.size() == source.size()")
+                    mk[i] = m
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        ptr = lambda a: a.ctypes.data_as(u8p) if a is not None else None
+        return rgb, depth, mk, (ptr(rgb), depth.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), rgb.shape[0], rgb.shape[1],
+                               ptr(mk[0]), ptr(mk[1]))
+
+    def upload_images(self, rgb, depth, masks=None):
+        keep = self._image_args(rgb, depth, masks)
+        check(self._L.lm_upload_images(self._h, *keep[3]))
+
+    def match_images(self, rgb, depth, masks, threshold):
+        keep = self._image_args(rgb, depth, masks)
+        cap = 1 << 14
+        while True:
+            out = np.zeros(cap, MATCH_DTYPE)
+            n = ctypes.c_int64()
+            rc = self._L.lm_match_images(self._h, *keep[3], ctypes.c_float(threshold), out.ctypes.data_as(ctypes.c_void_p), cap,
+                                         ctypes.byref(n))
+            if rc == LM_E_CAPACITY:
+                cap = int(n.value)
+                continue
+            check(rc)
+            return out[:n.value].copy()
+
+    def quantized(self, level, modality, shape):
+        out = np.zeros(shape, np.uint8)
+        check(self._L.lm_debug_quantized(self._h, level, modality, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), out.size))
+        return out
 
     def bind_quantized_device(self, ptrs, rows, cols):
         """ptrs: device addresses (ints) index level*2+modality; rows/cols per level."""

@@ -52,6 +52,20 @@ int lm_fail(int code, const char* fmt, ...) {
 }
 
 #include "lm_kernels.cuh"
+#include "lm_frontend.cuh"
+
+// Launch with programmatic stream serialization (see lm_pdl_wait in lm_kernels.cuh).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 
 // --------------------------------------------------------------------------------------------
 // host side
@@ -117,6 +131,15 @@ struct lm_detector {
   lm_result_header* h_res = nullptr; int64_t h_res_cap = 0;  // pinned staging: header + records
   int64_t h_valid = 0;                                       // records already copied to h_res
   float last_threshold = 0.f;
+
+  // GPU quantization front-end (lm_upload_images): per level colour image, unfiltered bins, gate, normals, masks
+  struct FeLevel {
+    int rows = 0, cols = 0;
+    uint8_t* src = nullptr; uint8_t* qun = nullptr; uint8_t* strong = nullptr; uint8_t* normal = nullptr;
+    uint8_t* mask[LM_MAX_MODALITIES] = {nullptr, nullptr};
+  } fe[LM_MAX_LEVELS];
+  uint16_t* fe_depth = nullptr; uint8_t* fe_nraw = nullptr;
+  bool fe_lut = false;
 
   bool timing = false;
   std::vector<cudaEvent_t> tev;  // timing slots x 5 events (ring)
@@ -184,6 +207,11 @@ extern "C" void lm_destroy(lm_detector* d) {
   cudaFree(d->d_mask); cudaFree(d->d_raw); cudaFree(d->d_cnt); cudaFree(d->d_off);
   cudaFree(d->d_res_own); cudaFree(d->d_counters);
   cudaFreeHost(d->h_counters); cudaFreeHost(d->h_res);
+  for (int l = 0; l < LM_MAX_LEVELS; ++l) {
+    cudaFree(d->fe[l].src); cudaFree(d->fe[l].qun); cudaFree(d->fe[l].strong); cudaFree(d->fe[l].normal);
+    cudaFree(d->fe[l].mask[0]); cudaFree(d->fe[l].mask[1]);
+  }
+  cudaFree(d->fe_depth); cudaFree(d->fe_nraw);
   for (cudaEvent_t e : d->tev) cudaEventDestroy(e);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
@@ -575,24 +603,103 @@ extern "C" int lm_bind_quantized_device(lm_detector* d, const uint8_t* const* d_
   return LM_OK;
 }
 
+// ---- GPU quantization front-end: Detector::match's modality processing (LL.cpp:1709-1741) -------------
+extern "C" int lm_upload_images(lm_detector* d, const uint8_t* rgb, const uint16_t* depth, int rows, int cols,
+                                const uint8_t* mask_color, const uint8_t* mask_depth) {
+  if (!d || !rgb || !depth) return fail(LM_E_INVALID, "null argument");
+  if (d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
+  CU(cudaSetDevice(d->device));
+  int lrows[LM_MAX_LEVELS], lcols[LM_MAX_LEVELS];
+  for (int l = 0; l < d->L; ++l) {
+    lrows[l] = l ? lrows[l - 1] / 2 : rows;  // Size(src.cols / 2, src.rows / 2), LL.cpp:564, 866
+    lcols[l] = l ? lcols[l - 1] / 2 : cols;
+  }
+  int rc = check_frame_dims(d, lrows, lcols);
+  if (rc) return rc;
+  rc = size_levels(d, lrows, lcols, true);
+  if (rc) return rc;
+  cudaStream_t st = d->stream;
+  if (!d->fe_lut) {
+    // NORMAL_LUT[.][vy][vx] of normal_lut.i: 45-degree sector (offset by half a sector) of atan2(vy-10, vx-10);
+    // the rule reproduces all 8000 entries of the reference table (tests/test_frontend.py)
+    uint8_t lut[400];
+    for (int vy = 0; vy < 20; ++vy)
+      for (int vx = 0; vx < 20; ++vx) {
+        double a = atan2((double)(vy - 10), (double)(vx - 10)) * 180.0 / 3.14159265358979323846;
+        a = fmod(a + 360.0, 360.0);
+        lut[vy * 20 + vx] = (uint8_t)(1u << (((int)(fmod(a + 22.5, 360.0) / 45.0)) % 8));
+      }
+    CU(cudaMemcpyToSymbolAsync(c_normal_lut, lut, sizeof(lut), 0, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    d->fe_lut = true;
+  }
+  for (int l = 0; l < d->L; ++l) {
+    lm_detector::FeLevel& f = d->fe[l];
+    if (f.rows != lrows[l] || f.cols != lcols[l]) {
+      cudaFree(f.src); cudaFree(f.qun); cudaFree(f.strong); cudaFree(f.normal); cudaFree(f.mask[0]); cudaFree(f.mask[1]);
+      f = lm_detector::FeLevel();
+      f.rows = lrows[l]; f.cols = lcols[l];
+      const size_t n = (size_t)f.rows * f.cols;
+      CU(cudaMalloc(&f.src, n * 3)); CU(cudaMalloc(&f.qun, n)); CU(cudaMalloc(&f.strong, n)); CU(cudaMalloc(&f.normal, n));
+      CU(cudaMalloc(&f.mask[0], n)); CU(cudaMalloc(&f.mask[1], n));
+      if (l == 0) {
+        cudaFree(d->fe_depth); cudaFree(d->fe_nraw);
+        CU(cudaMalloc(&d->fe_depth, n * 2)); CU(cudaMalloc(&d->fe_nraw, n));
+      }
+    }
+  }
+  const size_t n0 = (size_t)rows * cols;
+  CU(cudaMemcpyAsync(d->fe[0].src, rgb, n0 * 3, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d->fe_depth, depth, n0 * 2, cudaMemcpyHostToDevice, st));
+  const uint8_t* masks[2] = {mask_color, mask_depth};
+  for (int m = 0; m < 2; ++m)
+    if (masks[m]) CU(cudaMemcpyAsync(d->fe[0].mask[m], masks[m], n0, cudaMemcpyHostToDevice, st));
+  auto grid2 = [](int w, int h) { return dim3((unsigned)((w + 31) / 32), (unsigned)((h + 7) / 8)); };
+  for (int l = 0; l < d->L; ++l) {
+    lm_detector::FeLevel& f = d->fe[l];
+    LevelHost& lv = d->lv[l];
+    if (l > 0) {
+      lm_detector::FeLevel& up = d->fe[l - 1];
+      CU(launch_pdl(k_fe_pyrdown, grid2(f.cols, f.rows), dim3(256), 0, st, (const uint8_t*)up.src, up.rows, up.cols, f.src, f.rows, f.cols));
+      for (int m = 0; m < 2; ++m)
+        if (masks[m])
+          CU(launch_pdl(k_fe_decimate, grid2(f.cols, f.rows), dim3(256), 0, st, (const uint8_t*)up.mask[m], up.cols, f.mask[m], f.rows,
+                        f.cols, (const uint8_t*)nullptr, (uint8_t*)nullptr));
+      d->launches += 1 + (masks[0] ? 1 : 0) + (masks[1] ? 1 : 0);
+    }
+    // colour: weak threshold 10 -> gate on squared magnitude > 100 (ColorGradient(10, nf, 55), LL.cpp:1687)
+    CU(launch_pdl(k_fe_gradient, grid2(f.cols, f.rows), dim3(FE_TW, FE_TH), 0, st, (const uint8_t*)f.src, f.rows, f.cols, 100, f.qun, f.strong));
+    CU(launch_pdl(k_fe_hysteresis, grid2(f.cols, f.rows), dim3(256), 0, st, (const uint8_t*)f.qun, (const uint8_t*)f.strong,
+                  (const uint8_t*)(masks[0] ? f.mask[0] : nullptr), f.rows, f.cols, lv.d_q[0]));
+    d->launches += 2;
+    // depth: DepthNormal(2000, 50, nf, 2), LL.cpp:1688; upper levels decimate the LABELS (LL.cpp:865-868)
+    if (l == 0) {
+      CU(launch_pdl(k_fe_normals, grid2(f.cols, f.rows), dim3(256), 0, st, (const uint16_t*)d->fe_depth, f.rows, f.cols, 2000, 50, d->fe_nraw));
+      CU(launch_pdl(k_fe_median, grid2(f.cols, f.rows), dim3(256), 0, st, (const uint8_t*)d->fe_nraw,
+                    (const uint8_t*)(masks[1] ? f.mask[1] : nullptr), f.rows, f.cols, f.normal, lv.d_q[1]));
+      d->launches += 2;
+    } else {
+      lm_detector::FeLevel& up = d->fe[l - 1];
+      CU(launch_pdl(k_fe_decimate, grid2(f.cols, f.rows), dim3(256), 0, st, (const uint8_t*)up.normal, up.cols, f.normal, f.rows, f.cols,
+                    (const uint8_t*)(masks[1] ? f.mask[1] : nullptr), lv.d_q[1]));
+      d->launches += 1;
+    }
+    lv.q_src[0] = lv.d_q[0];
+    lv.q_src[1] = lv.d_q[1];
+  }
+  CU(cudaStreamSynchronize(st));  // the caller's images are only borrowed for the call
+  CU(cudaGetLastError());
+  d->have_frame = true;
+  d->have_run = false;
+  return LM_OK;
+}
+
 static LevelDev level_dev(const LevelHost& h) {
   LevelDev v;
   v.lm = h.d_lm; v.T = h.T; v.rows = h.rows; v.cols = h.cols; v.Wd = h.Wd; v.Hd = h.Hd; v.plane = h.plane;
   v.off = h.T / 2 + (h.T % 2 - 1);
   v.mod_stride = h.mod_stride;
   return v;
-}
-
-// Launch with programmatic stream serialization (see lm_pdl_wait in lm_kernels.cuh).
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 template <int R>
@@ -933,6 +1040,34 @@ extern "C" int lm_match_quantized(lm_detector* d, const uint8_t* const* quantize
   rc = lm_fetch_records(d, rec.data(), n, &got);
   if (rc) return rc;
   return lm_finish(d, rec.data(), got, out, cap, n_out);
+}
+
+extern "C" int lm_match_images(lm_detector* d, const uint8_t* rgb, const uint16_t* depth, int rows, int cols, const uint8_t* mask_color,
+                               const uint8_t* mask_depth, float threshold, lm_match* out, int64_t cap, int64_t* n_out) {
+  int rc = lm_upload_images(d, rgb, depth, rows, cols, mask_color, mask_depth);
+  if (rc) return rc;
+  rc = lm_run(d, threshold);
+  if (rc) return rc;
+  const int64_t n = d->h_res->count;
+  std::vector<lm_record> rec((size_t)n);
+  int64_t got = 0;
+  rc = lm_fetch_records(d, rec.data(), n, &got);
+  if (rc) return rc;
+  return lm_finish(d, rec.data(), got, out, cap, n_out);
+}
+
+extern "C" int lm_debug_quantized(lm_detector* d, int level, int modality, uint8_t* out, int64_t cap) {
+  if (!d || !out) return fail(LM_E_INVALID, "null argument");
+  if (d->device < 0) return fail(LM_E_STATE, "host-only handle");
+  if (!d->have_frame) return fail(LM_E_STATE, "no frame uploaded");
+  if (level < 0 || level >= d->L || modality < 0 || modality >= d->M) return fail(LM_E_INVALID, "bad level/modality");
+  const LevelHost& lv = d->lv[level];
+  const int64_t n = (int64_t)lv.rows * lv.cols;
+  if (n > cap) return fail(LM_E_CAPACITY, "need %lld bytes", (long long)n);
+  CU(cudaSetDevice(d->device));
+  CU(cudaMemcpyAsync(out, lv.q_src[modality], (size_t)n, cudaMemcpyDeviceToHost, d->stream));
+  CU(cudaStreamSynchronize(d->stream));
+  return LM_OK;
 }
 
 extern "C" int lm_debug_linear_memories(lm_detector* d, int level, int modality, uint8_t* out, int64_t cap) {

@@ -66,6 +66,9 @@ class Detector:
         self._selection = None
         self.device = _default_device()
         self.shard = (0, 1)  # (index, count): template shard matched by this process (multi-GPU)
+        # quantization front-end used by match(): "gpu" (CUDA, lm_match_images) or "cv2" (host, frontend.py);
+        # both produce the same label images (tests/test_gpu_frontend.py)
+        self.frontend = os.environ.get("LINEMOD_B200_FRONTEND", "gpu")
 
     # ---- template IO ----------------------------------------------------------------------
     def readClasses(self, class_ids, format):
@@ -135,10 +138,14 @@ class Detector:
         passes masks=[] (linemod_and_levelup_test.py:324)."""
         if masks is None:
             raise TypeError("match(): incompatible function arguments (masks must be a list; pass masks=[])")
+        if len(sources) != 2:
+            raise RuntimeError("sources.size() == modalities.size()")  # CV_Assert LL.cpp:1707
         sources = [self._as_source(s, i) for i, s in enumerate(sources)]
+        if self.frontend == "gpu" and self.shard[1] == 1:
+            nat = self._select(list(class_ids))
+            return self._to_matches(nat.match_images(sources[0], sources[1], list(masks), float(threshold)))
         quantized = self.quantize(sources, list(masks))
-        recs = self.match_quantized(quantized, threshold, class_ids)
-        return recs
+        return self.match_quantized(quantized, threshold, class_ids)
 
     def match_quantized(self, quantized, threshold, class_ids=()):
         """Same as match() but starting from quantized label images (the accelerated path proper)."""

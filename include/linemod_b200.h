@@ -95,6 +95,14 @@ int lm_upload_quantized(lm_detector* d, const uint8_t* const* quantized, const i
  * unchanged until the stages enqueued on them have completed).  No copy is made. */
 int lm_bind_quantized_device(lm_detector* d, const uint8_t* const* d_quantized, const int* rows, const int* cols);
 
+/* Frame upload from the RAW images, quantization front-end on the GPU: rgb u8 rows x cols x 3, depth u16
+ * rows x cols (mm), optional masks u8 rows x cols (255 = valid, NULL = none) -- the arguments of
+ * Detector::match (LL.cpp:1702-1719).  Produces the same label images as the reference's
+ * ColorGradientPyramid / DepthNormalPyramid (LL.cpp:350-505, 557-587, 729-886; parameters of
+ * Detector(num_features, T): weak threshold 10, distance 2000 mm, difference 50 mm). */
+int lm_upload_images(lm_detector* d, const uint8_t* rgb, const uint16_t* depth, int rows, int cols,
+                     const uint8_t* mask_color, const uint8_t* mask_depth);
+
 /* GPU stages on the uploaded frame: spread/response/linearize (LL.cpp:1094-1243), coarse similarity
  * scan + threshold (LL.cpp:1284-1354, 1836-1852), local 16x16 refinement up the pyramid
  * (LL.cpp:1366-1428, 1855-1938).  Leaves the ordered candidate records in device memory. */
@@ -126,7 +134,13 @@ int lm_finish(lm_detector* d, const lm_record* records, int64_t n, lm_match* out
 int lm_match_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols,
                        float threshold, lm_match* out, int64_t cap, int64_t* n_out);
 
+/* Detector::match proper (LL.cpp:1702-1777): raw images in, matches out. */
+int lm_match_images(lm_detector* d, const uint8_t* rgb, const uint16_t* depth, int rows, int cols, const uint8_t* mask_color,
+                    const uint8_t* mask_depth, float threshold, lm_match* out, int64_t cap, int64_t* n_out);
+
 /* ---- introspection used by the parity tests and the benchmark ---- */
+/* Quantized label image of (level, modality) of the uploaded frame: rows*cols bytes. */
+int lm_debug_quantized(lm_detector* d, int level, int modality, uint8_t* out, int64_t cap);
 /* Linear memories of (level, modality) of the last lm_run: [8][T*T][(cols/T)*(rows/T)] bytes. */
 int lm_debug_linear_memories(lm_detector* d, int level, int modality, uint8_t* out, int64_t cap);
 /* Counters of the last lm_run: [0] templates scanned, [1] coarse candidates, [2] algorithmic bytes of

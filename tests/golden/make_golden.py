@@ -78,3 +78,8 @@ def make_train_golden():
 
 if __name__ == "__main__":
     make_train_golden()
+    # frame_crop_case1.npz: a 400x320 window of the reference's fixture frame around the object (raw RGB-D,
+    # for the GPU front-end test)
+    rgb = cv2.imread(CASE + "0000_rgb.png")
+    dep = cv2.imread(CASE + "0000_dep.png", cv2.IMREAD_UNCHANGED)
+    np.savez_compressed(os.path.join(OUT, "frame_crop_case1.npz"), rgb=rgb[40:360, 200:600].copy(), dep=dep[40:360, 200:600].copy())
