@@ -135,3 +135,25 @@ def synth_frame(W=640, H=480, levels=2, seed=42, bank=None, plant=8, T=(4, 8)):
                     q[l][m][fy, fx] = (1 << t.features[:, 2]).astype(np.uint8)
             planted.append((cid, tid, x, y))
     return q, planted
+
+
+def synth_rgbd(W=640, H=480, seed=7):
+    """Structured raw RGB-D frame (u8 HxWx3, u16 HxW mm): smooth colour blobs with edges and noise; depth
+    planes, bumps, sensor holes and a far background -- exercises every branch of the quantization
+    front-end (used by the front-end tests and the front-end timing in bench.py)."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    rgb = np.zeros((H, W, 3), np.float32)
+    depth = np.full((H, W), 1200.0, np.float32) + 0.2 * xx + 0.1 * yy
+    for _ in range(12):
+        cx, cy, r = rng.uniform(0, W), rng.uniform(0, H), rng.uniform(15, 80)
+        m = ((xx - cx) ** 2 + (yy - cy) ** 2) < r * r
+        rgb[m] = rng.uniform(0, 255, 3)
+        depth[m] = rng.uniform(500, 1900) + 40 * np.sqrt(np.clip(1 - ((xx[m] - cx) ** 2 + (yy[m] - cy) ** 2) / (r * r), 0, 1))
+    rgb += rng.normal(0, 6, rgb.shape)
+    rgb = cv2.GaussianBlur(np.clip(rgb, 0, 255).astype(np.uint8), (3, 3), 0)
+    depth += rng.normal(0, 1.5, depth.shape)
+    depth[rng.random((H, W)) < 0.03] = 0   # sensor holes
+    depth[:, : W // 10] = 2600              # beyond the distance threshold
+    return rgb, np.clip(depth, 0, 65535).astype(np.uint16)

@@ -371,12 +371,45 @@ def main():
         "roofline": roofline,
         "counters": counters,
     }
+    if world == 1:
+        # quantization front-end (upstream of the metric): raw 640x480 RGB-D -> label pyramids, GPU kernels
+        # (incl. the 1.5 MB H2D of the raw frame) vs the cv2 calls the reference makes; identical outputs
+        synth = importlib.import_module("6dpose_b200.synth")
+        fe = importlib.import_module("6dpose_b200.frontend")
+        rgb, dep = synth.synth_rgbd(args.width, args.height, seed=5)
+        rgb_p = torch.from_numpy(rgb).pin_memory().numpy()
+        dep_p = torch.from_numpy(dep.view(np.int16)).pin_memory().numpy().view(np.uint16)
+        for _ in range(3):
+            nat.upload_images(rgb_p, dep_p)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            nat.upload_images(rgb_p, dep_p)
+        gpu_ms = (time.perf_counter() - t0) / 50 * 1e3
+        fe.quantize_pyramid([rgb, dep], 2)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            fe.quantize_pyramid([rgb, dep], 2)
+        cv2_ms = (time.perf_counter() - t0) / 5 * 1e3
+        t0 = time.perf_counter()
+        for _ in range(20):
+            mi = nat.match_images(rgb_p, dep_p, None, args.threshold)
+        mi_ms = (time.perf_counter() - t0) / 20 * 1e3
+        out["frontend"] = {"gpu_ms_per_frame": gpu_ms, "cv2_ms_per_frame": cv2_ms, "match_images_ms_per_frame": mi_ms,
+                           "note": "lm_upload_images (H2D of raw RGB-D + 9 kernels + sync) vs 6dpose_b200/frontend.py (cv2); "
+                                   "match_images = Detector::match from raw images through the C-ABI (lm_match_images)"}
     if not args.no_cpu_baseline and world == 1:
-        arms = cpu_arms(args, bank, frames, args.cpu_frames)
-        name, kind = best_cpu_arm(arms)
-        out["cpu_baseline"] = {"value": arms[name]["fps"], "unit": "frames/s", "cores": arms[name]["cores"], "kind": kind,
-                               "sample": "%d full frames of the same workload per arm; fastest arm reported (%s)" % (args.cpu_frames, name),
-                               "arms": arms}
+        # the CPU arm runs in its own process (torch's bundled OpenMP runtime in this one throttles the oracle's
+        # thread pool): same workload, same code path as `bench.py --impl reference`
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(max(args.cpu_frames, 1) * 4),
+               "--templates", str(args.templates), "--features", str(args.features), "--width", str(args.width),
+               "--height", str(args.height), "--threshold", str(args.threshold), "--seed", str(args.seed)]
+        env = dict(os.environ)
+        env.pop("OMP_NUM_THREADS", None)
+        try:
+            ref = json.loads(subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env).stdout.strip().split("\n")[-1])
+            out["cpu_baseline"] = ref["cpu_baseline"]
+        except Exception as e:  # the baseline is informative; never lose the GPU line over it
+            out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     emit(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -12,24 +12,6 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def synth_rgbd(rng, H, W):
-    """Structured RGB-D: smooth colour blobs with edges + noise, depth planes / bumps / holes / far background."""
-    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
-    rgb = np.zeros((H, W, 3), np.float32)
-    depth = np.full((H, W), 1200.0, np.float32) + 0.2 * xx + 0.1 * yy
-    for _ in range(12):
-        cx, cy, r = rng.uniform(0, W), rng.uniform(0, H), rng.uniform(15, 80)
-        m = ((xx - cx) ** 2 + (yy - cy) ** 2) < r * r
-        rgb[m] = rng.uniform(0, 255, 3)
-        depth[m] = rng.uniform(500, 1900) + 40 * np.sqrt(np.clip(1 - ((xx[m] - cx) ** 2 + (yy[m] - cy) ** 2) / (r * r), 0, 1))
-    rgb += rng.normal(0, 6, rgb.shape)
-    rgb = cv2.GaussianBlur(np.clip(rgb, 0, 255).astype(np.uint8), (3, 3), 0)
-    depth += rng.normal(0, 1.5, depth.shape)
-    depth[rng.random((H, W)) < 0.03] = 0          # sensor holes
-    depth[:, : W // 10] = 2600                     # beyond the distance threshold
-    return rgb, np.clip(depth, 0, 65535).astype(np.uint16)
-
-
 def test_phase_bins_match_opencv_on_the_whole_sobel_range():
     """The float model used by k_fe_gradient reproduces cv::phase's 16-bin quantisation for every
     (dx, dy) a 3x3 Sobel of a u8 image can produce (numpy float32 == separately rounded IEEE ops)."""
@@ -55,7 +37,7 @@ def test_gpu_front_end_equals_cv2_front_end(H, W, T, use_masks):
     lib = importlib.import_module("6dpose_b200._lib")
     fe = importlib.import_module("6dpose_b200.frontend")
     rng = np.random.default_rng(H + W + len(T))
-    rgb, depth = synth_rgbd(rng, H, W)
+    rgb, depth = importlib.import_module("6dpose_b200.synth").synth_rgbd(W, H, seed=H + W + len(T))
     masks = None
     if use_masks:
         m0 = np.zeros((H, W), np.uint8)
