@@ -205,9 +205,9 @@ class NativeDetector:
 
     def match_images(self, rgb, depth, masks, threshold):
         keep = self._image_args(rgb, depth, masks)
-        cap = 1 << 14
+        cap = 1 << 12
         while True:
-            out = np.zeros(cap, MATCH_DTYPE)
+            out = np.empty(cap, MATCH_DTYPE)
             n = ctypes.c_int64()
             rc = self._L.lm_match_images(self._h, *keep[3], ctypes.c_float(threshold), out.ctypes.data_as(ctypes.c_void_p), cap,
                                          ctypes.byref(n))
@@ -269,9 +269,9 @@ class NativeDetector:
 
     def match_quantized(self, quantized, threshold):
         qs, ptrs, r, c = self._frame_args(quantized)
-        cap = 1 << 14
+        cap = 1 << 12
         while True:
-            out = np.zeros(cap, MATCH_DTYPE)
+            out = np.empty(cap, MATCH_DTYPE)
             n = ctypes.c_int64()
             rc = self._L.lm_match_quantized(self._h, ptrs, r, c, ctypes.c_float(threshold),
                                             out.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(n))

@@ -562,7 +562,13 @@ static int size_levels(lm_detector* d, const int* rows, const int* cols, bool ne
   return LM_OK;
 }
 
+static int upload_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols, bool sync);
+
 extern "C" int lm_upload_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols) {
+  return upload_quantized(d, quantized, rows, cols, true);
+}
+
+static int upload_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols, bool sync) {
   if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
   if (!d || !quantized || !rows || !cols) return fail(LM_E_INVALID, "null argument");
   CU(cudaSetDevice(d->device));
@@ -579,7 +585,7 @@ extern "C" int lm_upload_quantized(lm_detector* d, const uint8_t* const* quantiz
       lv.q_src[m] = lv.d_q[m];
     }
   }
-  CU(cudaStreamSynchronize(d->stream));  // caller's buffers are only borrowed for the call
+  if (sync) CU(cudaStreamSynchronize(d->stream));  // caller's buffers are only borrowed for the call
   d->have_frame = true;
   d->have_run = false;
   return LM_OK;
@@ -1030,7 +1036,7 @@ extern "C" int lm_finish(lm_detector* d, const lm_record* records, int64_t n, lm
 
 extern "C" int lm_match_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols,
                                   float threshold, lm_match* out, int64_t cap, int64_t* n_out) {
-  int rc = lm_upload_quantized(d, quantized, rows, cols);
+  int rc = upload_quantized(d, quantized, rows, cols, false);  // lm_run synchronises before this call returns
   if (rc) return rc;
   rc = lm_run(d, threshold);
   if (rc) return rc;
