@@ -18,11 +18,14 @@ RECORD_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2"), ("similarity", "<f4"), ("wo
 HEADER_DTYPE = np.dtype([("count", "<i4"), ("coarse_candidates", "<i4"), ("capacity", "<i4"), ("shard", "<i4")])
 
 # every symbol include/linemod_b200.h declares (tests check the .so exports all of them)
+PEER_HANDLE_BYTES = 64
+
 SYMBOLS = [
     "lm_last_error", "lm_create", "lm_destroy", "lm_load_bank", "lm_select", "lm_shard_range",
     "lm_upload_quantized", "lm_upload_images", "lm_match_images", "lm_debug_quantized", "lm_bind_quantized_device", "lm_run", "lm_enqueue", "lm_complete", "lm_set_result_buffer", "lm_device_result", "lm_fetch_records",
     "lm_finish", "lm_match_quantized", "lm_debug_linear_memories", "lm_counters", "lm_set_timing",
     "lm_stage_times", "lm_stream", "lm_launch_count",
+    "lm_peer_export", "lm_peer_base", "lm_peer_connect", "lm_peer_connect_local", "lm_peer_disconnect",
     "lm_icp_create", "lm_icp_destroy", "lm_icp_process", "lm_icp_process_batch", "lm_icp_last_stats", "lm_icp_launch_count", "lm_icp_set_use_scene_cloud",
 ]
 
@@ -64,6 +67,11 @@ def load():
     L.lm_enqueue.argtypes = [vp, c_f]
     L.lm_complete.argtypes = [vp]
     L.lm_set_result_buffer.argtypes = [vp, vp, c_i64]
+    L.lm_peer_export.argtypes = [vp, c_int, c_i64, u8p_]
+    L.lm_peer_base.argtypes = [vp, ctypes.POINTER(vp)]
+    L.lm_peer_connect.argtypes = [vp, c_int, c_int, u8p_]
+    L.lm_peer_connect_local.argtypes = [vp, c_int, c_int, ctypes.POINTER(vp)]
+    L.lm_peer_disconnect.argtypes = [vp]
     L.lm_device_result.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(c_i64)]
     L.lm_fetch_records.argtypes = [vp, vp, c_i64, ctypes.POINTER(c_i64)]
     L.lm_finish.argtypes = [vp, vp, c_i64, vp, c_i64, ctypes.POINTER(c_i64)]
@@ -252,6 +260,33 @@ class NativeDetector:
 
     def set_result_buffer(self, device_ptr, capacity_records):
         check(self._L.lm_set_result_buffer(self._h, ctypes.c_void_p(device_ptr) if device_ptr else None, int(capacity_records)))
+
+    # ---- multi-GPU exchange fused into the refinement kernel (include/linemod_b200.h, lm_peer_*) ----
+    def peer_export(self, world, capacity_records=8192):
+        """Allocate this rank's exchange buffer; returns its CUDA IPC handle (bytes)."""
+        h = (ctypes.c_uint8 * PEER_HANDLE_BYTES)()
+        check(self._L.lm_peer_export(self._h, int(world), int(capacity_records), h))
+        return bytes(h)
+
+    def peer_base(self):
+        b = ctypes.c_void_p()
+        check(self._L.lm_peer_base(self._h, ctypes.byref(b)))
+        return b.value
+
+    def peer_connect(self, rank, world, handles):
+        """handles: list of `world` IPC handles (bytes), index = rank (own entry ignored)."""
+        blob = b"".join(bytes(h) for h in handles)
+        if len(blob) != world * PEER_HANDLE_BYTES:
+            raise ValueError("need %d handles of %d bytes" % (world, PEER_HANDLE_BYTES))
+        buf = (ctypes.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(self._L.lm_peer_connect(self._h, int(rank), int(world), buf))
+
+    def peer_connect_local(self, rank, world, bases):
+        arr = (ctypes.c_void_p * world)(*[int(b) for b in bases])
+        check(self._L.lm_peer_connect_local(self._h, int(rank), int(world), arr))
+
+    def peer_disconnect(self):
+        check(self._L.lm_peer_disconnect(self._h))
 
     def device_result(self):
         p, cap = ctypes.c_void_p(), ctypes.c_int64()

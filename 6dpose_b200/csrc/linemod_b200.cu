@@ -132,6 +132,16 @@ struct lm_detector {
   int64_t h_valid = 0;                                       // records already copied to h_res
   float last_threshold = 0.f;
 
+  // multi-GPU exchange fused into k_refine (lm_peer_*)
+  uint8_t* px_buf = nullptr;            // this rank's exchange buffer (IPC-exportable cudaMalloc)
+  int64_t px_cap = 0;                   // records per block
+  int px_world = 0, px_rank = -1;       // px_rank >= 0: connected
+  bool px_ipc = false;                  // peer bases opened with cudaIpcOpenMemHandle
+  uint8_t* px_base[LM_MAX_PEERS] = {nullptr};
+  int32_t px_seq = 0;
+  PeerExchange* d_px = nullptr;         // device copy of the descriptor (static after connect)
+  PeerExchange h_px;
+
   // GPU quantization front-end (lm_upload_images): per level colour image, unfiltered bins, gate, normals, masks
   struct FeLevel {
     int rows = 0, cols = 0;
@@ -190,10 +200,27 @@ extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** o
   CU(cudaGetDeviceProperties(&prop, device));
   d->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-  CU(cudaMalloc(&d->d_counters, 2 * sizeof(unsigned long long)));
-  CU(cudaMallocHost(&d->h_counters, 2 * sizeof(unsigned long long)));
+  CU(cudaMalloc(&d->d_counters, 4 * sizeof(unsigned long long)));
+  CU(cudaMemset(d->d_counters, 0, 4 * sizeof(unsigned long long)));
+  CU(cudaMallocHost(&d->h_counters, 4 * sizeof(unsigned long long)));
+  memset(d->h_counters, 0, 4 * sizeof(unsigned long long));
   *out = d;
   return LM_OK;
+}
+
+static void peer_release(lm_detector* d) {
+  if (d->px_ipc)
+    for (int r = 0; r < d->px_world; ++r)
+      if (r != d->px_rank && d->px_base[r]) cudaIpcCloseMemHandle(d->px_base[r]);
+  for (int r = 0; r < LM_MAX_PEERS; ++r) d->px_base[r] = nullptr;
+  d->px_rank = -1;
+  d->px_ipc = false;
+  if (d->px_buf) cudaFree(d->px_buf);
+  d->px_buf = nullptr;
+  if (d->d_px) cudaFree(d->d_px);
+  d->d_px = nullptr;
+  d->px_world = 0;
+  d->px_cap = 0;
 }
 
 extern "C" void lm_destroy(lm_detector* d) {
@@ -201,6 +228,7 @@ extern "C" void lm_destroy(lm_detector* d) {
   if (d->device < 0) { delete d; return; }
   cudaSetDevice(d->device);
   if (d->stream) cudaStreamSynchronize(d->stream);
+  peer_release(d);
   for (int l = 0; l < LM_MAX_LEVELS; ++l) free_level(d->lv[l]);
   cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_fdesc); cudaFree(d->d_work);
   cudaFree(d->d_items_bits); cudaFree(d->d_items_bytes); cudaFree(d->d_safe); cudaFree(d->d_galign);
@@ -727,6 +755,17 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
   const int n_work = (int)d->shard_count;
   const LevelHost& low = d->lv[d->L - 1];
   cudaStream_t st = d->stream;
+  // fused multi-GPU exchange: k_refine appends into block [frame slot][rank] of every rank's buffer
+  PeerExchange px;
+  memset(&px, 0, sizeof(px));
+  lm_result_header* px_block = nullptr;
+  if (d->px_rank >= 0) {
+    if (refine_only) return fail(LM_E_STATE, "refinement re-run is not available with a connected peer exchange");
+    ++d->px_seq;
+    px = d->h_px;
+    px_block = reinterpret_cast<lm_result_header*>(d->px_buf + (size_t)(d->px_seq & 1) * px.slot_bytes +
+                                                   (size_t)px.rank * px.block_bytes);
+  }
   if (d->timing && !refine_only) {
     d->ev = d->tev.data() + 5 * (size_t)(d->timing_runs % (int64_t)(d->tev.size() / 5));
     ++d->timing_runs;
@@ -814,7 +853,9 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[2], st));
-    CU(launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, (const int32_t*)d->d_cnt, d->d_off, n_work, d->d_res, (int)d->res_cap, d->shard_index, d->d_counters));
+    CU(launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, (const int32_t*)d->d_cnt, d->d_off, n_work,
+                  px.world > 0 ? px_block : d->d_res, (int)(px.world > 0 ? d->px_cap : d->res_cap), d->shard_index,
+                  d->d_counters));
     ++d->launches;
     if (d->timing) CU(cudaEventRecord(d->ev[3], st));
   }
@@ -832,10 +873,22 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     rp.work_begin = (int)d->shard_begin;
     rp.threshold = threshold;
     rp.hdr = d->d_res; rp.capacity = (int32_t)d->res_cap;
+    rp.px = px.world > 0 ? d->d_px : nullptr;
+    rp.px_seq = d->px_seq;
+    if (px.world > 0) {
+      rp.hdr = px_block;
+      rp.capacity = (int32_t)d->px_cap;
+    }
     rp.counters = d->d_counters;
     rp.safe = d->d_safe; rp.galign = d->d_galign;
     rp.bp_clear = low.d_bp; rp.bp_words = low.d_bp ? (uint32_t)((size_t)d->M * 8 * low.lbw) : 0u;
     CU(launch_pdl(k_refine, dim3(d->sm_count * 8), dim3(256), 0, st, rp));
+    ++d->launches;
+  }
+  if (px.world > 0) {
+    // collector: waits for all ranks' frame flags, packs the blocks into the ordinary result block
+    CU(launch_pdl(k_peer_collect, dim3(1), dim3(1024), 0, st, px, d->px_seq, (int32_t)d->px_cap, d->d_res, (int32_t)d->res_cap,
+                  d->d_counters + 2));
     ++d->launches;
   }
   if (d->timing) CU(cudaEventRecord(d->ev[4], st));
@@ -850,7 +903,7 @@ static int enqueue_readback(lm_detector* d) {
   const int64_t first = std::min<int64_t>(d->res_cap, LM_FIRST_FETCH);
   CU(cudaMemcpyAsync(d->h_res, d->d_res, sizeof(lm_result_header) + sizeof(lm_record) * (size_t)first,
                      cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(d->h_counters, d->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(d->h_counters, d->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   d->h_valid = first;
   return LM_OK;
 }
@@ -871,6 +924,13 @@ static int ensure_run_buffers(lm_detector* d) {
     d->d_raw = nullptr;
     d->raw_elems = need_r;
     CU(cudaMalloc(&d->d_raw, sizeof(uint16_t) * need_r));
+  }
+  if (d->px_rank >= 0 && d->res_external) return fail(LM_E_STATE, "lm_set_result_buffer and a connected peer exchange exclude each other");
+  if (d->px_rank >= 0 && d->res_cap_own < d->px_cap * d->px_world) {
+    cudaFree(d->d_res_own);
+    d->d_res_own = nullptr;
+    d->res_cap_own = d->px_cap * d->px_world;
+    CU(cudaMalloc(&d->d_res_own, sizeof(lm_result_header) + sizeof(lm_record) * (size_t)d->res_cap_own));
   }
   if (!d->res_external) {
     if (d->res_cap_own == 0) {
@@ -913,6 +973,12 @@ extern "C" int lm_complete(lm_detector* d) {
   if (rc) return rc;
   CU(cudaStreamSynchronize(d->stream));
   CU(cudaGetLastError());
+  if (d->px_rank >= 0) {
+    if (d->h_counters[2] == 1) return fail(LM_E_STATE, "peer exchange: a rank did not publish frame %d within the timeout", d->px_seq);
+    if (d->h_counters[2] == 2)
+      return fail(LM_E_CAPACITY, "peer exchange: a shard kept more than %lld records (capacity given to lm_peer_export)",
+                  (long long)d->px_cap);
+  }
   if ((int64_t)d->h_res->count > d->res_cap) {
     if (d->res_external)
       return fail(LM_E_CAPACITY, "%d records kept, caller's result buffer holds %lld", d->h_res->count, (long long)d->res_cap);
@@ -946,6 +1012,7 @@ extern "C" int lm_set_result_buffer(lm_detector* d, void* d_block, int64_t capac
   if (!d) return fail(LM_E_INVALID, "null detector");
   if (d_block && capacity_records < 1) return fail(LM_E_INVALID, "capacity must be >= 1");
   if (capacity_records > 0x7FFFFFFF) return fail(LM_E_INVALID, "capacity too large");
+  if (d_block && d->px_rank >= 0) return fail(LM_E_STATE, "lm_set_result_buffer and a connected peer exchange exclude each other");
   CU(cudaSetDevice(d->device));
   CU(cudaStreamSynchronize(d->stream));
   d->res_external = d_block != nullptr;
@@ -953,6 +1020,131 @@ extern "C" int lm_set_result_buffer(lm_detector* d, void* d_block, int64_t capac
     d->d_res = (lm_result_header*)d_block;
     d->res_cap = capacity_records;
   }
+  d->have_run = false;
+  return LM_OK;
+}
+
+static size_t peer_buffer_bytes(int world, int64_t cap) {
+  return 2 * (size_t)world * (sizeof(lm_result_header) + sizeof(lm_record) * (size_t)cap) +
+         sizeof(int32_t) * (2 * LM_MAX_PEERS + 4);
+}
+
+extern "C" int lm_peer_export(lm_detector* d, int world, int64_t capacity_records, uint8_t* handle_out) {
+  if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  if (world < 1 || world > LM_MAX_PEERS) return fail(LM_E_INVALID, "world %d outside 1..%d", world, LM_MAX_PEERS);
+  if (capacity_records < 1 || capacity_records > (1 << 24)) return fail(LM_E_INVALID, "capacity outside 1..2^24");
+  if (peer_buffer_bytes(world, capacity_records) > 0xF0000000ull) return fail(LM_E_INVALID, "exchange buffer too large");
+  CU(cudaSetDevice(d->device));
+  CU(cudaStreamSynchronize(d->stream));
+  peer_release(d);
+  const size_t bytes = peer_buffer_bytes(world, capacity_records);
+  CU(cudaMalloc(&d->px_buf, bytes));
+  CU(cudaMemset(d->px_buf, 0, bytes));
+  CU(cudaDeviceSynchronize());
+  d->px_world = world;
+  d->px_cap = capacity_records;
+  d->px_seq = 0;
+  if (handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) <= LM_PEER_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, d->px_buf));
+    memset(handle_out, 0, LM_PEER_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof(h));
+  }
+  return LM_OK;
+}
+
+extern "C" int lm_peer_base(lm_detector* d, void** base) {
+  if (!d || !base) return fail(LM_E_INVALID, "null argument");
+  if (!d->px_buf) return fail(LM_E_STATE, "lm_peer_export has not been called");
+  *base = d->px_buf;
+  return LM_OK;
+}
+
+static int peer_connect_common(lm_detector* d, int rank, int world) {
+  if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  if (!d->px_buf) return fail(LM_E_STATE, "lm_peer_export has not been called");
+  if (world != d->px_world) return fail(LM_E_INVALID, "world %d differs from the exported one (%d)", world, d->px_world);
+  if (rank < 0 || rank >= world) return fail(LM_E_INVALID, "rank %d outside 0..%d", rank, world - 1);
+  if (d->px_rank >= 0) return fail(LM_E_STATE, "already connected");
+  if (d->res_external) return fail(LM_E_STATE, "lm_set_result_buffer and the peer exchange exclude each other");
+  return LM_OK;
+}
+
+static int peer_upload_descriptor(lm_detector* d) {
+  PeerExchange px;
+  memset(&px, 0, sizeof(px));
+  for (int r = 0; r < d->px_world; ++r) px.base[r] = d->px_base[r];
+  px.world = d->px_world; px.rank = d->px_rank;
+  px.block_bytes = (uint32_t)(sizeof(lm_result_header) + sizeof(lm_record) * (size_t)d->px_cap);
+  px.slot_bytes = px.block_bytes * (uint32_t)d->px_world;
+  px.flags_offset = 2u * px.slot_bytes;
+  d->h_px = px;
+  if (!d->d_px) CU(cudaMalloc(&d->d_px, sizeof(PeerExchange)));
+  CU(cudaMemcpy(d->d_px, &px, sizeof(px), cudaMemcpyHostToDevice));
+  return LM_OK;
+}
+
+extern "C" int lm_peer_connect(lm_detector* d, int rank, int world, const uint8_t* handles) {
+  int rc = peer_connect_common(d, rank, world);
+  if (rc) return rc;
+  if (!handles) return fail(LM_E_INVALID, "null handles");
+  CU(cudaSetDevice(d->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { d->px_base[r] = d->px_buf; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * LM_PEER_HANDLE_BYTES, sizeof(h));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < r; ++q)
+        if (q != rank && d->px_base[q]) cudaIpcCloseMemHandle(d->px_base[q]);
+      for (int q = 0; q < LM_MAX_PEERS; ++q) d->px_base[q] = nullptr;
+      return fail(LM_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+    }
+    d->px_base[r] = (uint8_t*)ptr;
+  }
+  d->px_ipc = true;
+  d->px_rank = rank;
+  d->have_run = false;
+  return peer_upload_descriptor(d);
+}
+
+extern "C" int lm_peer_connect_local(lm_detector* d, int rank, int world, void* const* bases) {
+  int rc = peer_connect_common(d, rank, world);
+  if (rc) return rc;
+  if (!bases) return fail(LM_E_INVALID, "null bases");
+  CU(cudaSetDevice(d->device));
+  for (int r = 0; r < world; ++r) {
+    if (!bases[r]) return fail(LM_E_INVALID, "bases[%d] is null", r);
+    cudaPointerAttributes at;
+    CU(cudaPointerGetAttributes(&at, bases[r]));
+    if (at.type != cudaMemoryTypeDevice) return fail(LM_E_INVALID, "bases[%d] is not device memory", r);
+    if (at.device != d->device) {
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, d->device, at.device));
+      if (!can) return fail(LM_E_STATE, "device %d cannot access device %d", d->device, at.device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(LM_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+      (void)cudaGetLastError();
+    }
+    d->px_base[r] = (uint8_t*)bases[r];
+  }
+  d->px_base[rank] = d->px_buf;
+  d->px_ipc = false;
+  d->px_rank = rank;
+  d->have_run = false;
+  return peer_upload_descriptor(d);
+}
+
+extern "C" int lm_peer_disconnect(lm_detector* d) {
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  if (d->device < 0) return LM_OK;
+  CU(cudaSetDevice(d->device));
+  CU(cudaStreamSynchronize(d->stream));
+  peer_release(d);
   d->have_run = false;
   return LM_OK;
 }

@@ -632,7 +632,51 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
 // --------------------------------------------------------------------------------------------
 // K3: local refinement, one warp per coarse candidate, all upper pyramid levels
 // --------------------------------------------------------------------------------------------
+// Multi-GPU exchange fused into k_refine (include/linemod_b200.h, lm_peer_*): every rank's buffer is
+//   [2 frame slots][world result blocks of block_bytes] [2][LM_MAX_PEERS] int32 frame flags | int32 ticket
+// base[r] is rank r's buffer (a peer mapping over NVLink for r != rank).
+struct PeerExchange {
+  uint8_t* base[LM_MAX_PEERS];
+  int world, rank;         // world == 0: no exchange
+  uint32_t block_bytes;    // sizeof(lm_result_header) + capacity records
+  uint32_t slot_bytes;     // world * block_bytes
+  uint32_t flags_offset;   // byte offset of the flags
+};                         // frames carry a sequence number seq >= 1; frame slot = seq & 1
+
+// the exchange, record by record: the same slot of block [frame slot][rank] in every peer's buffer
+// (out of line: the rare path must not cost the scoring loop registers)
+static __device__ __noinline__ void peer_store_record(const PeerExchange* px, int seq, int slot, int4 r) {
+  const int world = px->world, rank = px->rank;
+  const size_t at = (size_t)(seq & 1) * px->slot_bytes + (size_t)rank * px->block_bytes + sizeof(lm_result_header) +
+                    (size_t)slot * sizeof(lm_record);
+  for (int q = 0; q < world; ++q)
+    if (q != rank) *reinterpret_cast<int4*>(px->base[q] + at) = r;
+}
+
+// publish: the last CTA to finish copies the header to every peer and raises this rank's frame flag there
+// (release: every CTA fences its peer stores before taking a ticket)
+static __device__ __noinline__ void peer_publish(const PeerExchange* px, int seq, const lm_result_header* hdr) {
+  const int world = px->world, rank = px->rank;
+  __threadfence_system();
+  int* ticket = reinterpret_cast<int*>(px->base[rank] + px->flags_offset) + 2 * LM_MAX_PEERS;
+  if (atomicAdd(ticket, 1) != (int)gridDim.x - 1) return;
+  *ticket = 0;
+  __threadfence();
+  const int4 h = __ldcg(reinterpret_cast<const int4*>(hdr));
+  const size_t blk = (size_t)(seq & 1) * px->slot_bytes + (size_t)rank * px->block_bytes;
+  for (int q = 0; q < world; ++q)
+    if (q != rank) *reinterpret_cast<int4*>(px->base[q] + blk) = h;
+  __threadfence_system();
+  for (int q = 0; q < world; ++q) {
+    volatile int32_t* flag =
+        reinterpret_cast<volatile int32_t*>(px->base[q] + px->flags_offset) + (seq & 1) * LM_MAX_PEERS + rank;
+    *flag = seq;
+  }
+}
+
 struct RefineParams {
+  const PeerExchange* px;  // device-resident descriptor of the fused multi-GPU exchange, or null
+  int32_t px_seq;          // this frame's sequence number
   LevelDev lv[LM_MAX_LEVELS];
   const TSlot* tslot;
   const uint32_t* fbase;
@@ -875,11 +919,77 @@ __global__ void __launch_bounds__(256, 4) k_refine(RefineParams p) {
         r.work = p.work_begin + w;
         r.seq = c;
         out[slot] = r;
+        if (p.px) peer_store_record(p.px, p.px_seq, slot, *reinterpret_cast<const int4*>(&r));
       }
     }
   }
   if (lane == 0 && feats_done) {
     atomicAdd(p.counters + 0, feats_done);
     atomicAdd(p.counters + 1, feats_read);
+  }
+  if (p.px) {
+    __syncthreads();
+    if (threadIdx.x == 0) peer_publish(p.px, p.px_seq, p.hdr);
+  }
+}
+
+// Collector of the fused exchange: waits until every rank's frame flag for `seq` has arrived in THIS rank's
+// buffer, then packs the `world` blocks of the frame slot into one ordinary result block (header.count =
+// all shards' kept records).  status: 0 ok, 1 a peer did not publish within the timeout, 2 a block
+// overflowed its capacity.  One CTA.
+__global__ void __launch_bounds__(1024) k_peer_collect(PeerExchange px, int32_t seq, int32_t block_capacity, lm_result_header* out_hdr,
+                                                       int32_t out_capacity, unsigned long long* status) {
+  lm_pdl_wait();
+  __shared__ int s_cnt[LM_MAX_PEERS + 1];
+  __shared__ int s_coarse[LM_MAX_PEERS];
+  __shared__ int s_status;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_status = 0;
+  __syncthreads();
+  const uint8_t* mine = px.base[px.rank];
+  if (tid < px.world) {
+    const volatile int32_t* flag = reinterpret_cast<const volatile int32_t*>(mine + px.flags_offset) +
+                                   (seq & 1) * LM_MAX_PEERS + tid;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    bool ok = true;
+    while ((int32_t)(*flag - seq) < 0) {
+      __nanosleep(200);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) { ok = false; break; }  // 20 s: a peer never enqueued this frame
+    }
+    __threadfence_system();  // acquire: the block contents were fenced before the flag
+    const lm_result_header* h = reinterpret_cast<const lm_result_header*>(
+        mine + (size_t)(seq & 1) * px.slot_bytes + (size_t)tid * px.block_bytes);
+    const int4 hv = ok ? __ldcv(reinterpret_cast<const int4*>(h)) : make_int4(0, 0, 0, 0);
+    if (!ok) atomicMax(&s_status, 1);
+    if (hv.x > block_capacity) atomicMax(&s_status, 2);
+    s_cnt[tid] = min(hv.x, block_capacity);
+    s_coarse[tid] = hv.y;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0, coarse = 0;
+    for (int r = 0; r < px.world; ++r) {
+      const int c = s_cnt[r];
+      s_cnt[r] = run;
+      run += c;
+      coarse += s_coarse[r];
+    }
+    s_cnt[px.world] = run;
+    out_hdr->count = run;
+    out_hdr->coarse_candidates = coarse;
+    out_hdr->capacity = out_capacity;
+    out_hdr->shard = -1;  // all shards
+    status[0] = (unsigned long long)s_status;
+  }
+  __syncthreads();
+  int4* out = reinterpret_cast<int4*>(out_hdr + 1);
+  for (int r = 0; r < px.world; ++r) {
+    const int4* src = reinterpret_cast<const int4*>(mine + (size_t)(seq & 1) * px.slot_bytes +
+                                                    (size_t)r * px.block_bytes + sizeof(lm_result_header));
+    const int b = s_cnt[r], n = s_cnt[r + 1] - b;
+    for (int i = tid; i < n; i += blockDim.x)
+      if (b + i < out_capacity) out[b + i] = __ldcv(src + i);  // peers wrote them: never from a stale L1 line
   }
 }

@@ -64,6 +64,7 @@ class Detector:
         self._bank_dirty = True
         self._class_order = []
         self._selection = None
+        self._peers = None  # (rank, world) once dist.connect_peers has wired the fused exchange
         self.device = _default_device()
         self.shard = (0, 1)  # (index, count): template shard matched by this process (multi-GPU)
         # quantization front-end used by match(): "gpu" (CUDA, lm_match_images) or "cv2" (host, frontend.py);

@@ -6,6 +6,12 @@ sequence (lm_select).  Every rank sees every frame.  The only exchange is ONE al
 per-rank result blocks (kept records, 16 bytes each, with their global (work, seq) sort keys); any
 rank can then run the host finisher (lm_finish = the reference's std::sort + std::unique) on the
 concatenation.  Backends: NCCL on device tensors (GPUs), gloo on host tensors (CPU tests).
+
+On GPUs the exchange is FUSED into the refinement kernel (connect_peers): k_refine stores every kept
+record straight into every rank's exchange buffer with peer stores over NVLink, a collector kernel on
+the same stream waits for all ranks' frame flags and packs the blocks -- the ordinary result block of
+each rank then already holds all shards' records; the process group only carries the one-time IPC
+handle exchange.
 """
 import numpy as np
 
@@ -39,6 +45,32 @@ def gather_records(records, group=None):
     return np.concatenate(parts) if parts else np.zeros(0, _lib.RECORD_DTYPE)
 
 
+def connect_peers(detector, group=None, capacity_records=8192, class_ids=()):
+    """One-time setup of the fused exchange: every rank exports its buffer's CUDA IPC handle, the
+    handles travel through the process group (any backend), every rank maps the others' buffers."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    detector.shard = shard_of(rank, world)
+    nat = detector._select(list(class_ids))
+    handle = nat.peer_export(world, capacity_records)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    nat.peer_connect(rank, world, handles)
+    dist.barrier(group=group)
+    detector._peers = (rank, world)
+    return nat
+
+
+def disconnect_peers(detector, group=None):
+    import torch.distributed as dist
+    if getattr(detector, "_peers", None) is None:
+        return
+    dist.barrier(group=group)  # nobody may still be storing into a buffer that is about to be unmapped
+    detector._native.peer_disconnect()
+    detector._peers = None
+    dist.barrier(group=group)
+
+
 def match_quantized_sharded(detector, quantized, threshold, class_ids=(), group=None):
     """Detector.match_quantized with the bank sharded over the process group: every rank returns the
     full, finished match list (identical to the single-GPU result)."""
@@ -48,6 +80,8 @@ def match_quantized_sharded(detector, quantized, threshold, class_ids=(), group=
     nat = detector._select(list(class_ids))
     nat.upload_quantized(quantized)
     nat.run(float(threshold))
-    local = nat.fetch_records()
-    allrec = gather_records(local, group)
+    if getattr(detector, "_peers", None) == (rank, world):
+        allrec = nat.fetch_records()  # fused exchange: the result block already holds every shard's records
+    else:
+        allrec = gather_records(nat.fetch_records(), group)
     return detector._to_matches(nat.finish(allrec))

@@ -120,6 +120,27 @@ int lm_complete(lm_detector* d);
 int lm_set_result_buffer(lm_detector* d, void* d_block, int64_t capacity_records);
 int lm_device_result(lm_detector* d, void** d_block, int64_t* capacity_records);
 
+/* Multi-GPU exchange fused into the refinement kernel (one process per GPU, template shards from
+ * lm_select; the reference has no counterpart: its template loop is serial, LL.cpp:1797).  Every rank
+ * owns an exchange buffer of 2 frame slots x `world` result blocks; once connected, k_refine stores every
+ * kept record into the block [slot][rank] of EVERY rank's buffer with peer stores over NVLink (local
+ * stores for itself), its last CTA publishes the block header and a frame sequence flag, and a collector
+ * kernel on the same stream waits for all `world` flags and packs the blocks into this handle's result
+ * block.  lm_complete / lm_fetch_records / lm_device_result then see the kept records of ALL shards: no
+ * separate collective, no host round trip between refinement and exchange.  All ranks must enqueue the
+ * same frames in the same order (SPMD); capacity_records is per rank and per frame.
+ *   lm_peer_export        allocate the buffer, return its CUDA IPC handle (LM_PEER_HANDLE_BYTES bytes)
+ *   lm_peer_connect       handles[world][LM_PEER_HANDLE_BYTES] of all ranks (own entry ignored)
+ *   lm_peer_connect_local same, for handles living in ONE process: bases[world] from lm_peer_base
+ *   lm_peer_disconnect    back to the single-GPU result block (callers barrier first) */
+#define LM_PEER_HANDLE_BYTES 64
+#define LM_MAX_PEERS 16
+int lm_peer_export(lm_detector* d, int world, int64_t capacity_records, uint8_t* handle_out);
+int lm_peer_base(lm_detector* d, void** base);
+int lm_peer_connect(lm_detector* d, int rank, int world, const uint8_t* handles);
+int lm_peer_connect_local(lm_detector* d, int rank, int world, void* const* bases);
+int lm_peer_disconnect(lm_detector* d);
+
 /* Copy the kept records of the last completed run to the host, sorted by (work, seq). */
 int lm_fetch_records(lm_detector* d, lm_record* out, int64_t cap, int64_t* n_out);
 

@@ -22,7 +22,7 @@ def free_port():
     return p
 
 
-def worker(rank, world, port, out_dir):
+def worker(rank, world, port, out_dir, fused=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -38,14 +38,22 @@ def worker(rank, world, port, out_dir):
     det = pkg.Detector(150, T)
     det.device = 0
     det.bank = bank
+    if fused:
+        # exchange fused into k_refine: IPC handles over the process group, then no collective at all
+        dmod.connect_peers(det, capacity_records=4096)
+        for s in (7, 8):  # earlier frames: both frame slots and the sequence flags get used
+            q0, _ = synth.synth_frame(640, 480, seed=s, bank=bank, plant=3, T=T)
+            dmod.match_quantized_sharded(det, q0, 75.0, [])
     got = dmod.match_quantized_sharded(det, q, 75.0, [])
+    c = det._native.counters()
+    if fused:
+        dmod.disconnect_peers(det)
     want = oracle.match(q, T, bank.pack(bank.class_ids(), 4), 75.0)
     ids = bank.class_ids()
     ok = len(got) == len(want) and len(want) > 50
     for g, w in zip(got, want):
         ok = ok and (g.x, g.y, g.template_id, g.class_id) == (int(w["x"]), int(w["y"]), int(w["template_id"]), ids[int(w["class_idx"])])
         ok = ok and np.float32(g.similarity) == w["similarity"]
-    c = det._native.counters()
     np.save(os.path.join(out_dir, "ok_%d.npy" % rank), np.asarray([int(ok), len(got), c["templates"]]))
     dist.destroy_process_group()
 
@@ -56,3 +64,82 @@ def test_two_rank_sharded_cuda_match(tmp_path):
     res = [np.load(os.path.join(str(tmp_path), "ok_%d.npy" % r)) for r in range(2)]
     assert all(r[0] == 1 for r in res), res
     assert sum(int(r[2]) for r in res) == 240   # the two shards cover the bank
+
+
+def test_two_rank_fused_exchange_ipc(tmp_path):
+    """Same, with the exchange fused into the refinement kernel (peer stores through CUDA IPC mappings,
+    collector kernel instead of the all-gather)."""
+    port = free_port()
+    mp.spawn(worker, args=(2, port, str(tmp_path), True), nprocs=2, join=True)
+    res = [np.load(os.path.join(str(tmp_path), "ok_%d.npy" % r)) for r in range(2)]
+    assert all(r[0] == 1 for r in res), res
+    assert sum(int(r[2]) for r in res) == 240
+
+
+def test_fused_exchange_three_handles_one_process():
+    """Three shards as three handles (three streams) of one process on cuda:0, connected through raw device
+    pointers: every handle's result block holds all shards' records, identical to the unsharded run, over
+    several frames (slot / sequence reuse), with records landing in a different order every time."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    synth = importlib.import_module("6dpose_b200.synth")
+    lib = importlib.import_module("6dpose_b200._lib")
+    T = [4, 8]
+    bank = synth.synth_bank(150, num_features=150, seed=51, class_ids=("01_template", "02_template", "03_template"))
+    packed = bank.pack(bank.class_ids(), 4)
+    world = 3
+    single = lib.NativeDetector(T, 0)
+    single.load_bank(packed, 4)
+    single.select(None, 0, 1)
+    dets = []
+    for r in range(world):
+        d = lib.NativeDetector(T, 0)
+        d.load_bank(packed, 4)
+        d.select(None, r, world)
+        d.peer_export(world, 4096)
+        dets.append(d)
+    bases = [d.peer_base() for d in dets]
+    for r, d in enumerate(dets):
+        d.peer_connect_local(r, world, bases)
+    for seed in (61, 62, 63, 64, 65):
+        q, _ = synth.synth_frame(640, 480, seed=seed, bank=bank, plant=5, T=T)
+        single.upload_quantized(q)
+        single.run(75.0)
+        want = single.fetch_records()
+        assert len(want) > 30
+        for d in dets:
+            d.upload_quantized(q)
+        for d in dets:
+            d.enqueue(75.0)
+        for d in dets:
+            d.complete()
+        for d in dets:
+            got = d.fetch_records()
+            assert len(got) == len(want)
+            for f in ("x", "y", "similarity", "work"):  # seq is the candidate index inside the shard
+                assert np.array_equal(got[f], want[f]), f
+        assert single.finish(want).tobytes() == dets[1].finish(dets[1].fetch_records()).tobytes()
+    # a block too small for its shard's records is reported, not truncated silently
+    for d in dets:
+        d.peer_disconnect()
+    for d in dets:
+        d.peer_export(world, 2)
+    bases = [d.peer_base() for d in dets]
+    for r, d in enumerate(dets):
+        d.peer_connect_local(r, world, bases)
+    for d in dets:
+        d.upload_quantized(q)
+    for d in dets:
+        d.enqueue(75.0)
+    with pytest.raises(lib.LinemodLibraryError, match="capacity"):
+        dets[0].complete()
+    for d in dets[1:]:
+        with pytest.raises(lib.LinemodLibraryError):
+            d.complete()
+    for d in dets:
+        d.peer_disconnect()
+    # back to the ordinary single-handle path
+    dets[0].select(None, 0, 1)
+    dets[0].upload_quantized(q)
+    dets[0].run(75.0)
+    assert dets[0].fetch_records().tobytes() == want.tobytes()
