@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--ring", type=int, default=176, help="distinct frames cycled through (176 x 768 KB > 126 MB L2)")
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the same workload timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: record exchange fused into the refinement kernel (peer stores over NVLink) or one "
+                         "NCCL all-gather of result blocks per frame (the baseline)")
     ap.add_argument("--seed", type=int, default=1234)
     return ap.parse_args()
 
@@ -177,6 +180,8 @@ def workload_config(args, n):
                         % (args.templates, args.features, args.width, args.height, args.threshold),
             "templates": args.templates, "frame": [args.width, args.height], "threshold": args.threshold,
             "parallelism": "template-shard x%d" % n,
+            "exchange": "none" if n == 1 else ("fused into k_refine (peer stores over NVLink + collector kernel)"
+                                               if args.exchange == "fused" else "nccl all-gather of result blocks"),
             "l2": "ring of %d distinct frames (%.0f MB of label images > 126 MB L2); bank and linear memories are "
                   "L2-resident by design" % (args.ring, args.ring * (args.width * args.height * 2 * 1.25) / 1e6)}
 
@@ -227,18 +232,28 @@ def main():
         ring.append((ts, [t.data_ptr() for t in ts]))
     stream = torch.cuda.ExternalStream(nat.stream(), device=local)
 
-    # result block: torch-owned so that it can be the NCCL all-gather send buffer
     cap = 16384
     blk_bytes = 16 + 16 * cap
-    res = torch.zeros(blk_bytes, dtype=torch.uint8, device="cuda")
-    nat.set_result_buffer(res.data_ptr(), cap)
-    gathered = torch.zeros(world * blk_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
+    fused = world > 1 and args.exchange == "fused"
+    res = gathered = None
+    if fused:
+        # exchange fused into k_refine: peer stores into every rank's exchange buffer (CUDA IPC mappings over
+        # NVLink) + a collector kernel; the process group only carries the IPC handles, once
+        handles = [None] * world
+        dist.all_gather_object(handles, nat.peer_export(world, cap))
+        nat.peer_connect(rank, world, handles)
+        dist.barrier()
+    elif world > 1:
+        # baseline exchange: torch-owned result block = the send buffer of one NCCL all-gather per frame
+        res = torch.zeros(blk_bytes, dtype=torch.uint8, device="cuda")
+        nat.set_result_buffer(res.data_ptr(), cap)
+        gathered = torch.zeros(world * blk_bytes, dtype=torch.uint8, device="cuda")
 
     def step(i):
         ts, ptrs = ring[i % len(ring)]
         nat.bind_quantized_device(ptrs, rows, cols)
         nat.enqueue(args.threshold)
-        if world > 1:
+        if world > 1 and not fused:
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(gathered, res)
 
@@ -287,8 +302,6 @@ def main():
     barrier()
 
     # ---- e2e: host buffers through the C-ABI match call ------------------------------------------
-    if world == 1:
-        nat.set_result_buffer(0, 0)
     host_frames = []
     for q in frames[:min(len(frames), 64)]:
         hq = [[torch.from_numpy(np.ascontiguousarray(q[l][m])).pin_memory().numpy() for m in range(2)] for l in range(2)]
@@ -297,8 +310,8 @@ def main():
 
     def e2e_step(i):
         q = host_frames[i % len(host_frames)]
-        if world == 1:
-            return nat.match_quantized(q, args.threshold)
+        if world == 1 or fused:
+            return nat.match_quantized(q, args.threshold)   # the blocking C-ABI call, host buffers in and out
         nat.upload_quantized(q)
         nat.enqueue(args.threshold)
         with torch.cuda.stream(stream):
@@ -328,6 +341,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     e2e_fps = n_e2e / dt
+    if fused:
+        barrier()
+        nat.peer_disconnect()
+        barrier()
 
     if rank != 0:
         if dist is not None:
