@@ -73,15 +73,22 @@ class Detector:
 
     # ---- template IO ----------------------------------------------------------------------
     def readClasses(self, class_ids, format):
-        """Detector::readClasses, LL.cpp:2124-2134 (format is a printf pattern with one %s)."""
+        """Detector::readClasses, LL.cpp:2124-2134 (format is a printf pattern with one %s).
+
+        Beyond the reference: a pattern ending in ".lmb" names packed bank files (bank.py), and with
+        LINEMOD_B200_BANK_CACHE=1 a YAML is read through a packed sibling `<file>.lmb` (built on first use)."""
         for cid in class_ids:
-            self.bank.read_class(format % cid, self.pyramid_levels)
+            self.bank.read_any(format % cid, self.pyramid_levels)
         self._bank_dirty = True
 
     def writeClasses(self, format):
-        """Detector::writeClasses, LL.cpp:2136-2146."""
+        """Detector::writeClasses, LL.cpp:2136-2146 (".lmb" pattern: packed bank files)."""
+        from .bank import PACKED_SUFFIX
         for cid in self.bank.class_ids():
-            self.bank.write_class(cid, format % cid, self.pyramid_levels)
+            if (format % cid).endswith(PACKED_SUFFIX):
+                self.bank.write_packed(cid, format % cid, self.pyramid_levels)
+            else:
+                self.bank.write_class(cid, format % cid, self.pyramid_levels)
 
     def addTemplate(self, sources, class_id, object_mask):
         """Detector::addTemplate, LL.cpp:1943-1975: returns the template id, or -1 on failure."""

@@ -159,6 +159,8 @@ def add_template(detector, sources, class_id, object_mask):
         if mask.dtype != np.uint8:
             raise TypeError("object_mask must be uint8 (255 = object)")
     pyramids = detector.bank.classes.setdefault(class_id, [])  # class_templates[class_id], even on failure
+    if not isinstance(pyramids, list):  # loaded from a packed bank file: unpack before growing it
+        pyramids = detector.bank.classes[class_id] = list(pyramids)
     template_id = len(pyramids)
     L = detector.pyramid_levels
     nf = detector.num_features

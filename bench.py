@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--ring", type=int, default=176, help="distinct frames cycled through (176 x 768 KB > 126 MB L2)")
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the same workload timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=3,
+                    help="frames in flight per GPU for `value`: one handle (stream + buffers) per lane, frames "
+                         "alternate between lanes so that the small kernels of one frame fill the tail of another")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: record exchange fused into the refinement kernel (peer stores over NVLink) or one "
                          "NCCL all-gather of result blocks per frame (the baseline)")
@@ -179,7 +182,7 @@ def workload_config(args, n):
                         "T=[4,8], %dx%d quantized RGB-D frames, threshold %g, 8 planted templates per frame"
                         % (args.templates, args.features, args.width, args.height, args.threshold),
             "templates": args.templates, "frame": [args.width, args.height], "threshold": args.threshold,
-            "parallelism": "template-shard x%d" % n,
+            "parallelism": "template-shard x%d" % n, "lanes": args.lanes,
             "exchange": "none" if n == 1 else ("fused into k_refine (peer stores over NVLink + collector kernel)"
                                                if args.exchange == "fused" else "nccl all-gather of result blocks"),
             "l2": "ring of %d distinct frames (%.0f MB of label images > 126 MB L2); bank and linear memories are "
@@ -219,9 +222,13 @@ def main():
     lib = importlib.import_module("6dpose_b200._lib")
     bank, frames = make_workload(args, args.ring)
     packed = bank.pack(bank.class_ids(), 4)
-    nat = lib.NativeDetector(T_PYR, device=local)
-    nat.load_bank(packed, 4)
-    nat.select(None, rank, world)
+    nats = []
+    for _ in range(max(1, args.lanes)):
+        n_ = lib.NativeDetector(T_PYR, device=local)
+        n_.load_bank(packed, 4)
+        n_.select(None, rank, world)
+        nats.append(n_)
+    nat = nats[0]
 
     # frame ring resident in HBM (torch owns the memory; the library borrows the pointers)
     rows = [args.height, args.height // 2]
@@ -231,6 +238,7 @@ def main():
         ts = [torch.from_numpy(np.ascontiguousarray(q[l][m])).cuda() for l in range(2) for m in range(2)]
         ring.append((ts, [t.data_ptr() for t in ts]))
     stream = torch.cuda.ExternalStream(nat.stream(), device=local)
+    lane_streams = [torch.cuda.ExternalStream(n_.stream(), device=local) for n_ in nats]
 
     cap = 16384
     blk_bytes = 16 + 16 * cap
@@ -239,9 +247,10 @@ def main():
     if fused:
         # exchange fused into k_refine: peer stores into every rank's exchange buffer (CUDA IPC mappings over
         # NVLink) + a collector kernel; the process group only carries the IPC handles, once
-        handles = [None] * world
-        dist.all_gather_object(handles, nat.peer_export(world, cap))
-        nat.peer_connect(rank, world, handles)
+        for n_ in nats:
+            handles = [None] * world
+            dist.all_gather_object(handles, n_.peer_export(world, cap))
+            n_.peer_connect(rank, world, handles)
         dist.barrier()
     elif world > 1:
         # baseline exchange: torch-owned result block = the send buffer of one NCCL all-gather per frame
@@ -251,8 +260,9 @@ def main():
 
     def step(i):
         ts, ptrs = ring[i % len(ring)]
-        nat.bind_quantized_device(ptrs, rows, cols)
-        nat.enqueue(args.threshold)
+        n_ = nats[i % len(nats)] if (fused or world == 1) else nat
+        n_.bind_quantized_device(ptrs, rows, cols)
+        n_.enqueue(args.threshold)
         if world > 1 and not fused:
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(gathered, res)
@@ -262,25 +272,37 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    def complete_all():
+        for n_ in nats:
+            n_.complete()
+
+    def join_lanes():
+        # the timing stream (lane 0) waits for the other lanes' work issued so far
+        for ls in lane_streams[1:]:
+            ev = torch.cuda.Event()
+            ev.record(ls)
+            stream.wait_event(ev)
+
+    for i in range(max(args.warmup, 3) * len(nats)):
         step(i)
-    nat.complete()
+    complete_all()
     barrier()
 
     # ---- timed region: K steps, device resident --------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = nat.launch_count()
+    launches0 = sum(n_.launch_count() for n_ in nats)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
     for i in range(args.steps):
         step(args.warmup + i)
+    join_lanes()
     e1.record(stream)
-    nat.complete()
+    complete_all()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = nat.launch_count() - launches0
+    launches = sum(n_.launch_count() for n_ in nats) - launches0
     clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([ms], device="cuda")
@@ -293,12 +315,16 @@ def main():
     counters = nat.counters()
 
     # ---- per-kernel durations over K more steps (CUDA events on the launching stream) ------------
+    all_lanes, nats = nats, nats[:1]     # one lane: stage durations without overlap
     nat.set_timing(min(args.steps, 256))
+    if fused and len(all_lanes) > 1:
+        barrier()
     for i in range(min(args.steps, 256)):
         step(args.warmup + i)
     nat.complete()
     stage = nat.stage_times_us()
     nat.set_timing(0)
+    nats = all_lanes
     barrier()
 
     # ---- e2e: host buffers through the C-ABI match call ------------------------------------------
@@ -347,9 +373,39 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     e2e_fps = n_e2e / dt
+
+    # the same blocking call from several host threads, one handle (stream) per thread: what a caller serving
+    # several cameras gets; reported beside e2e, not instead of it
+    conc = None
+    if len(nats) > 1 and (world == 1 or fused):
+        import threading
+
+        def caller(n_, k, cnt):
+            for i in range(cnt):
+                n_.match_quantized(host_frames[(k + i * len(nats)) % len(host_frames)], args.threshold)
+
+        def run_callers(cnt):
+            th = [threading.Thread(target=caller, args=(n_, k, cnt)) for k, n_ in enumerate(nats)]
+            t0 = time.perf_counter()
+            for t_ in th:
+                t_.start()
+            for t_ in th:
+                t_.join()
+            return time.perf_counter() - t0
+
+        run_callers(3)
+        barrier()
+        dtc = run_callers(n_e2e)
+        if world > 1:
+            t = torch.tensor([dtc], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtc = float(t.item())
+        conc = {"threads": len(nats), "value": n_e2e * len(nats) / dtc, "unit": "frames/s",
+                "note": "blocking lm_match_quantized from %d host threads, one handle each" % len(nats)}
     if fused:
         barrier()
-        nat.peer_disconnect()
+        for n_ in nats:
+            n_.peer_disconnect()
         barrier()
 
     if rank != 0:
@@ -401,7 +457,7 @@ def main():
         "dtype": "u8/u16", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // max(n_e2e, 1),
-                "steps": n_e2e, "passes_s": passes, "api": "lm_match_quantized (C-ABI), pinned host label images -> matches"},
+                "steps": n_e2e, "passes_s": passes, "concurrent_callers": conc, "api": "lm_match_quantized (C-ABI), pinned host label images -> matches"},
         "gpu_launches": launches,
         "roofline": roofline,
         "counters": counters,
