@@ -25,6 +25,7 @@ SYMBOLS = [
     "lm_upload_quantized", "lm_upload_images", "lm_match_images", "lm_debug_quantized", "lm_bind_quantized_device", "lm_run", "lm_enqueue", "lm_complete", "lm_set_result_buffer", "lm_device_result", "lm_fetch_records",
     "lm_finish", "lm_match_quantized", "lm_debug_linear_memories", "lm_counters", "lm_set_timing",
     "lm_stage_times", "lm_stream", "lm_launch_count",
+    "lm_set_boxes", "lm_enqueue_post", "lm_complete_post", "lm_match_top",
     "lm_peer_export", "lm_peer_base", "lm_peer_connect", "lm_peer_connect_local", "lm_peer_disconnect",
     "lm_icp_create", "lm_icp_destroy", "lm_icp_process", "lm_icp_process_batch", "lm_icp_last_stats", "lm_icp_launch_count", "lm_icp_set_use_scene_cloud",
 ]
@@ -67,6 +68,11 @@ def load():
     L.lm_enqueue.argtypes = [vp, c_f]
     L.lm_complete.argtypes = [vp]
     L.lm_set_result_buffer.argtypes = [vp, vp, c_i64]
+    L.lm_set_boxes.argtypes = [vp, i32p, c_i64]
+    L.lm_enqueue_post.argtypes = [vp, ctypes.c_double, c_int]
+    L.lm_complete_post.argtypes = [vp, vp, c_i64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
+    L.lm_match_top.argtypes = [vp, u8pp, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_f, ctypes.c_double, c_int, vp, c_i64,
+                               ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
     L.lm_peer_export.argtypes = [vp, c_int, c_i64, u8p_]
     L.lm_peer_base.argtypes = [vp, ctypes.POINTER(vp)]
     L.lm_peer_connect.argtypes = [vp, c_int, c_int, u8p_]
@@ -315,6 +321,32 @@ class NativeDetector:
                 continue
             check(rc)
             return out[:n.value].copy()
+
+    # ---- post-match stage on the device: greedy NMS + top-k (include/linemod_b200.h, lm_*_post) ----
+    def set_boxes(self, wh):
+        if wh is None:
+            check(self._L.lm_set_boxes(self._h, None, 0))
+            return
+        wh = np.ascontiguousarray(wh, np.int32).reshape(-1, 2)
+        check(self._L.lm_set_boxes(self._h, self._i32(wh), wh.shape[0]))
+
+    def enqueue_post(self, iou_threshold=0.5, top_k=3):
+        check(self._L.lm_enqueue_post(self._h, float(iou_threshold), int(top_k)))
+
+    def complete_post(self):
+        out = np.empty(1024, MATCH_DTYPE)
+        n, nrec = ctypes.c_int64(), ctypes.c_int64()
+        check(self._L.lm_complete_post(self._h, out.ctypes.data_as(ctypes.c_void_p), out.shape[0], ctypes.byref(n),
+                                       ctypes.byref(nrec)))
+        return out[:n.value].copy(), int(nrec.value)
+
+    def match_top(self, quantized, threshold, iou_threshold=0.5, top_k=3):
+        qs, ptrs, r, c = self._frame_args(quantized)
+        out = np.empty(1024, MATCH_DTYPE)
+        n, nrec = ctypes.c_int64(), ctypes.c_int64()
+        check(self._L.lm_match_top(self._h, ptrs, r, c, ctypes.c_float(threshold), float(iou_threshold), int(top_k),
+                                   out.ctypes.data_as(ctypes.c_void_p), out.shape[0], ctypes.byref(n), ctypes.byref(nrec)))
+        return out[:n.value].copy(), int(nrec.value)
 
     def linear_memories(self, level, modality, shape):
         out = np.zeros(shape, np.uint8)

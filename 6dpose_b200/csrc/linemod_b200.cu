@@ -53,6 +53,7 @@ int lm_fail(int code, const char* fmt, ...) {
 
 #include "lm_kernels.cuh"
 #include "lm_frontend.cuh"
+#include "lm_post.cuh"
 
 // Launch with programmatic stream serialization (see lm_pdl_wait in lm_kernels.cuh).
 template <typename... KArgs, typename... Args>
@@ -131,6 +132,14 @@ struct lm_detector {
   lm_result_header* h_res = nullptr; int64_t h_res_cap = 0;  // pinned staging: header + records
   int64_t h_valid = 0;                                       // records already copied to h_res
   float last_threshold = 0.f;
+
+  // post-match stage (lm_post.cuh): greedy NMS on the device, top-k survivors to the host
+  std::vector<int32_t> boxes;           // [G][2] caller's box sizes (empty: L0 template width/height)
+  PostInfo* d_post_info = nullptr; int64_t post_info_n = 0; bool post_dirty = true;
+  lm_match* d_post_out = nullptr; lm_match* h_post_out = nullptr;  // LM_POST_MAX survivors
+  int32_t* d_post_counts = nullptr; int32_t* h_post_counts = nullptr;
+  uint8_t* d_post_live = nullptr; int64_t post_live_cap = 0;
+  bool post_pending = false;
 
   // multi-GPU exchange fused into k_refine (lm_peer_*)
   uint8_t* px_buf = nullptr;            // this rank's exchange buffer (IPC-exportable cudaMalloc)
@@ -235,6 +244,8 @@ extern "C" void lm_destroy(lm_detector* d) {
   cudaFree(d->d_mask); cudaFree(d->d_raw); cudaFree(d->d_cnt); cudaFree(d->d_off);
   cudaFree(d->d_res_own); cudaFree(d->d_counters);
   cudaFreeHost(d->h_counters); cudaFreeHost(d->h_res);
+  cudaFree(d->d_post_info); cudaFree(d->d_post_out); cudaFree(d->d_post_counts); cudaFree(d->d_post_live);
+  cudaFreeHost(d->h_post_out); cudaFreeHost(d->h_post_counts);
   for (int l = 0; l < LM_MAX_LEVELS; ++l) {
     cudaFree(d->fe[l].src); cudaFree(d->fe[l].qun); cudaFree(d->fe[l].strong); cudaFree(d->fe[l].normal);
     cudaFree(d->fe[l].mask[0]); cudaFree(d->fe[l].mask[1]);
@@ -283,6 +294,8 @@ extern "C" int lm_load_bank(lm_detector* d, int n_classes, const int32_t* class_
   d->G = G;
   d->class_begin.assign(class_begin, class_begin + n_classes + 1);
   d->tmeta.assign(tmeta, tmeta + (size_t)G * n_slots * 4);
+  d->boxes.clear();  // box sizes belong to the bank they were set for
+  d->post_dirty = true;
   d->feats.assign(feats, feats + (size_t)n_feats * 3);
   d->feat_slot.swap(slot_of);
   cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_fdesc);
@@ -350,6 +363,7 @@ extern "C" int lm_select(lm_detector* d, const int32_t* class_sel, int n_classes
   d->shard_count = cut(shard_index + 1) - d->shard_begin;
   d->sel.swap(sel);  // after the cuts: the lambda reads `sel`
   d->work_dirty = true;
+  d->post_dirty = true;
   d->have_run = false;
   return LM_OK;
 }
@@ -486,6 +500,7 @@ static int prepare_bank(lm_detector* d) {
   for (int l = 0; l < d->L; ++l) { d->prep_rows[l] = d->lv[l].rows; d->prep_cols[l] = d->lv[l].cols; }
   d->prepared = true;
   d->work_dirty = true;
+  d->post_dirty = true;
   return LM_OK;
 }
 
@@ -1224,6 +1239,135 @@ extern "C" int lm_finish(lm_detector* d, const lm_record* records, int64_t n, lm
     out[i].class_index = v[i].class_index; out[i].template_id = v[i].template_id;
   }
   return LM_OK;
+}
+
+// ---- post-match stage -------------------------------------------------------------
+#define LM_POST_MAX 1024
+
+extern "C" int lm_set_boxes(lm_detector* d, const int32_t* wh, int64_t n_templates) {
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  if (!wh) {
+    d->boxes.clear();
+  } else {
+    if (n_templates != d->G) return fail(LM_E_INVALID, "%lld box sizes for a bank of %d templates", (long long)n_templates, d->G);
+    for (int64_t i = 0; i < 2 * n_templates; ++i)
+      if (wh[i] < 0 || wh[i] > 32767) return fail(LM_E_INVALID, "box size outside 0..32767");
+    d->boxes.assign(wh, wh + 2 * n_templates);
+  }
+  d->post_dirty = true;
+  return LM_OK;
+}
+
+static int prepare_post(lm_detector* d) {
+  if (!d->d_post_out) {
+    CU(cudaMalloc(&d->d_post_out, sizeof(lm_match) * LM_POST_MAX));
+    CU(cudaMallocHost(&d->h_post_out, sizeof(lm_match) * LM_POST_MAX));
+    CU(cudaMalloc(&d->d_post_counts, sizeof(int32_t) * 4));
+    CU(cudaMallocHost(&d->h_post_counts, sizeof(int32_t) * 4));
+  }
+  if (d->post_live_cap < d->res_cap) {
+    cudaFree(d->d_post_live);
+    d->d_post_live = nullptr;
+    d->post_live_cap = d->res_cap;
+    CU(cudaMalloc(&d->d_post_live, (size_t)d->post_live_cap));
+  }
+  if (!d->post_dirty) return LM_OK;
+  if (!d->boxes.empty() && (int64_t)d->boxes.size() != 2 * (int64_t)d->G) {
+    d->boxes.clear();  // the bank changed under the caller's boxes
+    return fail(LM_E_STATE, "box sizes were set for another bank: call lm_set_boxes again");
+  }
+  const int64_t n = (int64_t)d->sel.size();
+  std::vector<int> class_of(d->G);
+  for (int c = 0; c < d->n_classes; ++c)
+    for (int g = d->class_begin[c]; g < d->class_begin[c + 1]; ++g) class_of[g] = c;
+  std::vector<PostInfo> info((size_t)std::max<int64_t>(n, 1));
+  for (int64_t i = 0; i < n; ++i) {
+    const int g = d->sel[i];
+    PostInfo& q = info[i];
+    q.class_index = class_of[g];
+    q.template_id = g - d->class_begin[class_of[g]];
+    if (d->boxes.empty()) {  // Template::width / height of the first modality at level 0 (LL.h:36-45)
+      q.width = d->tmeta[((size_t)g * d->S) * 4 + 0];
+      q.height = d->tmeta[((size_t)g * d->S) * 4 + 1];
+    } else {
+      q.width = d->boxes[2 * (size_t)g];
+      q.height = d->boxes[2 * (size_t)g + 1];
+    }
+  }
+  if (d->post_info_n < (int64_t)info.size()) {
+    cudaFree(d->d_post_info);
+    d->d_post_info = nullptr;
+    d->post_info_n = (int64_t)info.size();
+    CU(cudaMalloc(&d->d_post_info, sizeof(PostInfo) * info.size()));
+  }
+  CU(cudaMemcpyAsync(d->d_post_info, info.data(), sizeof(PostInfo) * info.size(), cudaMemcpyHostToDevice, d->stream));
+  CU(cudaStreamSynchronize(d->stream));
+  d->post_dirty = false;
+  return LM_OK;
+}
+
+extern "C" int lm_enqueue_post(lm_detector* d, double iou_threshold, int top_k) {
+  if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  if (!d->d_res) return fail(LM_E_STATE, "no stages enqueued (call lm_enqueue first)");
+  if (top_k > LM_POST_MAX) return fail(LM_E_INVALID, "top_k %d > %d", top_k, LM_POST_MAX);
+  if (!(iou_threshold >= 0.0)) return fail(LM_E_INVALID, "IoU threshold must be >= 0");
+  if (d->sel.empty()) return fail(LM_E_STATE, "empty selection");
+  CU(cudaSetDevice(d->device));
+  int rc = prepare_post(d);
+  if (rc) return rc;
+  PostParams p;
+  p.hdr = d->d_res; p.capacity = (int32_t)d->res_cap;
+  p.info = d->d_post_info; p.n_sel = (int32_t)d->sel.size();
+  p.iou_threshold = iou_threshold; p.top_k = top_k;
+  p.out = d->d_post_out; p.out_capacity = LM_POST_MAX;
+  p.out_counts = d->d_post_counts; p.live = d->d_post_live;
+  CU(launch_pdl(k_post_nms, dim3(1), dim3(1024), 0, d->stream, p));
+  ++d->launches;
+  d->post_pending = true;
+  return LM_OK;
+}
+
+extern "C" int lm_complete_post(lm_detector* d, lm_match* out, int64_t cap, int64_t* n_out, int64_t* n_records) {
+  if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
+  if (!d || !n_out) return fail(LM_E_INVALID, "null argument");
+  if (!d->post_pending) return fail(LM_E_STATE, "lm_enqueue_post has not been called");
+  CU(cudaSetDevice(d->device));
+  cudaStream_t st = d->stream;
+  CU(cudaMemcpyAsync(d->h_post_counts, d->d_post_counts, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));
+  // the common top-k is small: fetch a first window with the counts, the rest only if there is more
+  const int first = 16;
+  CU(cudaMemcpyAsync(d->h_post_out, d->d_post_out, sizeof(lm_match) * first, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(d->h_counters, d->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  d->post_pending = false;
+  if (d->px_rank >= 0 && d->h_counters[2] == 1) return fail(LM_E_STATE, "peer exchange: a rank did not publish frame %d within the timeout", d->px_seq);
+  if (d->px_rank >= 0 && d->h_counters[2] == 2) return fail(LM_E_CAPACITY, "peer exchange: a shard kept more than %lld records", (long long)d->px_cap);
+  const int64_t n = d->h_post_counts[0];
+  if (n_records) *n_records = d->h_post_counts[1];
+  if ((int64_t)d->h_post_counts[1] > d->res_cap)
+    return fail(LM_E_CAPACITY, "%d records kept, the result block holds %lld: the NMS did not see all of them", d->h_post_counts[1],
+                (long long)d->res_cap);
+  *n_out = n;
+  if (n > cap) return fail(LM_E_CAPACITY, "%lld survivors, capacity %lld", (long long)n, (long long)cap);
+  if (n > first) {
+    CU(cudaMemcpyAsync(d->h_post_out + first, d->d_post_out + first, sizeof(lm_match) * (size_t)(n - first), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  if (n > 0 && out) memcpy(out, d->h_post_out, sizeof(lm_match) * (size_t)n);
+  return LM_OK;
+}
+
+extern "C" int lm_match_top(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols, float threshold,
+                            double iou_threshold, int top_k, lm_match* out, int64_t cap, int64_t* n_out, int64_t* n_records) {
+  int rc = upload_quantized(d, quantized, rows, cols, false);
+  if (rc) return rc;
+  rc = lm_enqueue(d, threshold);
+  if (rc) return rc;
+  rc = lm_enqueue_post(d, iou_threshold, top_k);
+  if (rc) return rc;
+  return lm_complete_post(d, out, cap, n_out, n_records);
 }
 
 extern "C" int lm_match_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols,

@@ -161,6 +161,31 @@ class Detector:
         out = nat.match_quantized(quantized, float(threshold))
         return self._to_matches(out)
 
+    # ---- post-match stage (the reference's drivers do this on the host) ----
+    def setBoxes(self, sizes):
+        """Box size (width, height) per template for the NMS: dict class_id -> array [n_templates, 2], as the
+        drivers' template-info files give it (linemod_and_levelup_test.py:248-249, 337-338).  None = the
+        templates' own width/height."""
+        nat = self._ensure_native()
+        if sizes is None:
+            nat.set_boxes(None)
+            return
+        rows = []
+        for cid in self._class_order:
+            wh = np.asarray(sizes[cid], np.int32).reshape(-1, 2)
+            if wh.shape[0] != self.bank.num_templates(cid):
+                raise ValueError("class %s: %d box sizes for %d templates" % (cid, wh.shape[0], self.bank.num_templates(cid)))
+            rows.append(wh)
+        nat.set_boxes(np.concatenate(rows, 0))
+
+    def match_top(self, quantized, threshold, class_ids=(), iou_threshold=0.5, top_k=3):
+        """match + nms(dets, iou_threshold)[:top_k] of the reference's drivers (linemod_and_levelup_test.py:
+        34-61, 325-350) in one call; the NMS runs on the GPU and only the survivors are copied back.
+        Returns (list[Match] best first, number of raw matches before sort/unique)."""
+        nat = self._select(list(class_ids))
+        out, nrec = nat.match_top(quantized, float(threshold), float(iou_threshold), int(top_k))
+        return self._to_matches(out), nrec
+
     def _to_matches(self, out):
         res = []
         for r in out:

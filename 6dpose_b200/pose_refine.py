@@ -60,3 +60,33 @@ class poseRefine:
 
     def getT(self):
         return self._t
+
+
+def refine_matches(sceneDepth, sceneK, matches, modelDepths, modelKs, modelRs, modelTs, device=None):
+    """The drivers' loop over the NMS survivors (linemod_and_levelup_test.py:348-367: one poseRefine per
+    match, fed with the render of the matched template's pose) as ONE batched GPU call: hypothesis i is
+    matches[i] (its x, y) with modelDepths[i] / modelKs[i] / modelRs[i] / modelTs[i].  Returns a list of
+    poseRefine objects in the state process() would have left them in."""
+    n = len(matches)
+    out = [poseRefine() for _ in range(n)]
+    if n == 0:
+        return out
+    scene = np.asarray(sceneDepth)
+    if scene.dtype != np.uint16 or scene.ndim != 2:
+        raise TypeError("sceneDepth must be a uint16 HxW depth image (mm)")
+    models = [np.asarray(m) for m in modelDepths]
+    if len(models) != n or any(m.dtype != np.uint16 or m.ndim != 2 for m in models):
+        raise TypeError("modelDepths: one uint16 HxW render per match")
+    sK = poseRefine._mat(sceneK, np.float32, (3, 3), "sceneK")
+    mK = np.stack([poseRefine._mat(k, np.float32, (3, 3), "modelK") for k in modelKs])
+    R = np.stack([poseRefine._mat(r, np.float32, (3, 3), "modelR") for r in modelRs])
+    t = np.stack([poseRefine._mat(v, np.float32, (3,), "modelT") for v in modelTs])
+    xy = [[int(m.x), int(m.y)] for m in matches]
+    dev = out[0].device if device is None else int(device)
+    Ro, to, res = _native(dev).process_batch(scene, models, sK, mK, R, t, xy, poseRefine.max_iterations)
+    for i, p in enumerate(out):
+        p._residual = float(res[i])
+        if res[i] != -1.0:
+            p._R = Ro[i].copy()
+            p._t = to[i].reshape(3, 1).copy()
+    return out

@@ -150,6 +150,25 @@ int lm_fetch_records(lm_detector* d, lm_record* out, int64_t cap, int64_t* n_out
  * records in any order. */
 int lm_finish(lm_detector* d, const lm_record* records, int64_t n, lm_match* out, int64_t cap, int64_t* n_out);
 
+/* Post-match stage on the device.  The reference's callers turn the match list into boxes
+ * (x, y, x+width, y+height, similarity), run a greedy NMS at IoU 0.5 and refine the first three survivors
+ * with poseRefine (linemod_and_levelup_test.py:34-61, 325-367; linemod_ros/detect.py:41-81, 94-134).  Here
+ * the NMS runs on the device behind the refinement kernel, on the kept records where they lie (all shards'
+ * records with a connected peer exchange), and only the top_k survivors are copied to the host.
+ *   lm_set_boxes      wh[n_templates][2]: box size per template in bank order (the drivers take it from their
+ *                     template-info files); NULL / never called = Template::width/height of level 0 (LL.h:36-45)
+ *   lm_enqueue_post   after lm_enqueue, same stream; top_k <= 0 = every survivor (at most 1024)
+ *   lm_complete_post  waits; out[n_out] in pick order (best first); n_records = kept records the NMS saw
+ *   lm_match_top      lm_upload_quantized + lm_enqueue + lm_enqueue_post + lm_complete_post
+ * IoU as in the reference's nms(): float64, "+1" pixel convention, suppressed when ovr > threshold.  Equal
+ * similarities (whose order the reference leaves to an unstable sort) are taken in template_id, class, y, x
+ * order. */
+int lm_set_boxes(lm_detector* d, const int32_t* wh, int64_t n_templates);
+int lm_enqueue_post(lm_detector* d, double iou_threshold, int top_k);
+int lm_complete_post(lm_detector* d, lm_match* out, int64_t cap, int64_t* n_out, int64_t* n_records);
+int lm_match_top(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols, float threshold,
+                 double iou_threshold, int top_k, lm_match* out, int64_t cap, int64_t* n_out, int64_t* n_records);
+
 /* Convenience = lm_upload_quantized + lm_run + lm_fetch_records + lm_finish (single GPU):
  * Detector::match after quantization. */
 int lm_match_quantized(lm_detector* d, const uint8_t* const* quantized, const int* rows, const int* cols,

@@ -109,3 +109,28 @@ def test_icp_batch_equals_single_calls_and_iteration_cap():
     R0, t0, r0 = icp.process_batch(scene, [models[1]], K, K[None], Rs[:1], ts[:1], [xy[1]], max_iterations=0)
     want = icp_oracle.pose_refine(scene, models[1], K, K, Rs[0], ts[0], xy[1][0], xy[1][1], max_iter=0, use_scene_cloud=True)
     assert rel(t0[0], want["t"]) <= TOL
+
+
+def test_refine_matches_batch_equals_single_calls(gold):
+    """The NMS-survivor hand-off: one batched call == the drivers' per-match loop."""
+    mod = importlib.import_module("linemodLevelup_pybind")
+    pr = importlib.import_module("6dpose_b200.pose_refine")
+    det = importlib.import_module("6dpose_b200.detector")
+    names = ("scene_a", "scene_b", "scene_edge")
+    ms = []
+    for nme in names:
+        m = det.Match()
+        m.x, m.y = [int(v) for v in gold["xy_" + nme]]
+        ms.append(m)
+    n = len(ms)
+    got = pr.refine_matches(gold["scene"], gold["K"], ms, [gold["model"]] * n, [gold["K"]] * n, [gold["R"]] * n,
+                            [gold["t"]] * n)
+    for m, g in zip(ms, got):
+        p = mod.poseRefine()
+        p.process(gold["scene"], gold["model"], gold["K"], gold["K"], gold["R"], gold["t"], m.x, m.y)
+        assert g.getResidual() == p.getResidual()
+        if p.getR() is None:
+            assert g.getR() is None and g.getT() is None
+        else:
+            assert np.array_equal(g.getR(), p.getR()) and np.array_equal(g.getT(), p.getT())
+    assert pr.refine_matches(gold["scene"], gold["K"], [], [], [], [], []) == []
