@@ -253,9 +253,9 @@ class NativeDetector:
         check(self._L.lm_complete(self._h))
 
     def fetch_records(self):
-        cap = 1 << 16
+        cap = 1 << 12
         while True:
-            out = np.zeros(cap, RECORD_DTYPE)
+            out = np.empty(cap, RECORD_DTYPE)
             n = ctypes.c_int64()
             rc = self._L.lm_fetch_records(self._h, out.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(n))
             if rc == LM_E_CAPACITY:

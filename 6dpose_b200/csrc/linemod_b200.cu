@@ -133,6 +133,10 @@ struct lm_detector {
   int64_t h_valid = 0;                                       // records already copied to h_res
   float last_threshold = 0.f;
 
+  std::vector<int> class_of;            // template -> class (lm_finish), rebuilt when the bank changes
+  std::vector<int32_t> order_cnt;       // order_records scratch
+  std::vector<lm_record> order_tmp, finish_rec;
+
   // post-match stage (lm_post.cuh): greedy NMS on the device, top-k survivors to the host
   std::vector<int32_t> boxes;           // [G][2] caller's box sizes (empty: L0 template width/height)
   PostInfo* d_post_info = nullptr; int64_t post_info_n = 0; bool post_dirty = true;
@@ -294,6 +298,7 @@ extern "C" int lm_load_bank(lm_detector* d, int n_classes, const int32_t* class_
   d->G = G;
   d->class_begin.assign(class_begin, class_begin + n_classes + 1);
   d->tmeta.assign(tmeta, tmeta + (size_t)G * n_slots * 4);
+  d->class_of.clear();
   d->boxes.clear();  // box sizes belong to the bank they were set for
   d->post_dirty = true;
   d->feats.assign(feats, feats + (size_t)n_feats * 3);
@@ -1177,6 +1182,44 @@ static bool record_order(const lm_record& a, const lm_record& b) {
   return a.seq < b.seq;
 }
 
+// (work, seq) order = the order in which the reference's loops produce the matches (LL.cpp:1797-1939).  The
+// records arrive grouped by nothing (atomic append) but with few per template: one counting pass over `work`
+// and an insertion sort by `seq` inside each template's run -- O(n + templates) instead of n log n compares.
+static void order_records(lm_detector* d, lm_record* r, int64_t n) {
+  if (n < 2 || std::is_sorted(r, r + n, record_order)) return;
+  const int64_t n_sel = (int64_t)d->sel.size();
+  bool in_range = n_sel > 0 && n_sel <= (1 << 22);
+  for (int64_t i = 0; in_range && i < n; ++i) in_range = r[i].work >= 0 && r[i].work < n_sel;
+  if (!in_range) {
+    std::sort(r, r + n, record_order);
+    return;
+  }
+  std::vector<int32_t>& cnt = d->order_cnt;
+  cnt.assign((size_t)n_sel + 1, 0);
+  for (int64_t i = 0; i < n; ++i) ++cnt[(size_t)r[i].work + 1];
+  for (int64_t w = 0; w < n_sel; ++w) cnt[(size_t)w + 1] += cnt[(size_t)w];
+  std::vector<lm_record>& tmp = d->order_tmp;
+  tmp.resize((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {  // place, keeping each run sorted by seq
+    const int32_t w = r[i].work;
+    int32_t at = cnt[(size_t)w]++;
+    tmp[(size_t)at] = r[i];
+  }
+  // cnt[w] is now the END of run w; runs are short: insertion sort by seq
+  int32_t b = 0;
+  for (int64_t w = 0; w < n_sel; ++w) {
+    const int32_t e = cnt[(size_t)w];
+    for (int32_t i = b + 1; i < e; ++i) {
+      const lm_record x = tmp[(size_t)i];
+      int32_t j = i - 1;
+      while (j >= b && tmp[(size_t)j].seq > x.seq) { tmp[(size_t)j + 1] = tmp[(size_t)j]; --j; }
+      tmp[(size_t)j + 1] = x;
+    }
+    b = e;
+  }
+  memcpy(r, tmp.data(), sizeof(lm_record) * (size_t)n);
+}
+
 extern "C" int lm_fetch_records(lm_detector* d, lm_record* out, int64_t cap, int64_t* n_out) {
   if (!d || !n_out) return fail(LM_E_INVALID, "null argument");
   if (!d->have_run) return fail(LM_E_STATE, "lm_run has not been called");
@@ -1193,7 +1236,7 @@ extern "C" int lm_fetch_records(lm_detector* d, lm_record* out, int64_t cap, int
   }
   if (n > 0) {
     memcpy(out, h, sizeof(lm_record) * (size_t)n);
-    std::sort(out, out + n, record_order);  // the reference's pre-sort order
+    order_records(d, out, n);  // the reference's pre-sort order
   }
   return LM_OK;
 }
@@ -1215,11 +1258,15 @@ struct HostMatch {  // LL.h:225-258 with class_index standing in for the class_i
 
 extern "C" int lm_finish(lm_detector* d, const lm_record* records, int64_t n, lm_match* out, int64_t cap, int64_t* n_out) {
   if (!d || !n_out || (n > 0 && !records)) return fail(LM_E_INVALID, "null argument");
-  std::vector<int> class_of(d->G);
-  for (int c = 0; c < d->n_classes; ++c)
-    for (int g = d->class_begin[c]; g < d->class_begin[c + 1]; ++g) class_of[g] = c;
-  std::vector<lm_record> rec(records, records + n);
-  std::sort(rec.begin(), rec.end(), record_order);  // class order -> template_id -> coarse cell (LL.cpp:1797-1939)
+  if ((int)d->class_of.size() != d->G) {
+    d->class_of.resize((size_t)d->G);
+    for (int c = 0; c < d->n_classes; ++c)
+      for (int g = d->class_begin[c]; g < d->class_begin[c + 1]; ++g) d->class_of[(size_t)g] = c;
+  }
+  const std::vector<int>& class_of = d->class_of;
+  std::vector<lm_record>& rec = d->finish_rec;
+  rec.assign(records, records + n);
+  order_records(d, rec.data(), n);  // class order -> template_id -> coarse cell (LL.cpp:1797-1939)
   std::vector<HostMatch> v;
   v.reserve((size_t)n);
   for (int64_t i = 0; i < n; ++i) {

@@ -374,6 +374,23 @@ def main():
         dt = float(t.item())
     e2e_fps = n_e2e / dt
 
+    # the drivers' next step (NMS at IoU 0.5, first three survivors) fused behind the match: lm_match_top
+    top3 = None
+    if world == 1 or fused:
+        for i in range(3):
+            nat.match_top(host_frames[i % len(host_frames)], args.threshold, 0.5, 3)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            nat.match_top(host_frames[i % len(host_frames)], args.threshold, 0.5, 3)
+        dtt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dtt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtt = float(t.item())
+        top3 = {"value": n_e2e / dtt, "unit": "frames/s",
+                "note": "lm_match_top: match + greedy NMS (IoU 0.5) + top-3 on the device, 60 bytes back"}
+
     # the same blocking call from several host threads, one handle (stream) per thread: what a caller serving
     # several cameras gets; reported beside e2e, not instead of it
     conc = None
@@ -457,7 +474,7 @@ def main():
         "dtype": "u8/u16", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // max(n_e2e, 1),
-                "steps": n_e2e, "passes_s": passes, "concurrent_callers": conc, "api": "lm_match_quantized (C-ABI), pinned host label images -> matches"},
+                "steps": n_e2e, "passes_s": passes, "concurrent_callers": conc, "match_top3": top3, "api": "lm_match_quantized (C-ABI), pinned host label images -> matches"},
         "gpu_launches": launches,
         "roofline": roofline,
         "counters": counters,
