@@ -691,7 +691,7 @@ struct RefineParams {
   lm_result_header* hdr;  // result block: header, then `capacity` records
   int32_t capacity;
   unsigned long long* counters;  // [0] features x candidates of the reference's refinement (x256 = algorithmic
-                                 // bytes), [1] features actually read (early exit)
+                                 // bytes), [1] feature x patch rows actually read (row-wise early exit; x16 bytes)
   const uint8_t* safe;           // per template: no feature can leave the image once a clamped patch
                                  // offset is applied (LL.cpp:1394 never skips) -> 128-bit row loads
   const uint16_t* galign;        // [G][S][16]: features per (fbase & 15) group (refined levels are stored
@@ -703,14 +703,20 @@ struct RefineParams {
 // One lane pair = one row of the 16x16 patch: lane `half` loads the aligned 16-byte chunk (a >> 4) +
 // half; K = word offset of the row start inside the first chunk.  The lane then needs the words
 // K + 2*half .. K + 2*half + 2 of the 8-word pair and gets the ones it lacks from its partner.
+#ifndef LM_REFINE_CHECK
+#define LM_REFINE_CHECK 21  // features between two early-exit tests of the refinement (<= 63)
+#endif
+
 template <int K>
 __device__ __forceinline__ void refine_rows(const uint4* __restrict__ lm128, const uint32_t* __restrict__ fb, int n,
-                                            uint32_t shift_row, int half, uint32_t sh, uint32_t& a8, uint32_t& b8) {
+                                            uint32_t shift_row, int half, uint32_t sh, bool alive, uint32_t& a8,
+                                            uint32_t& b8) {
   const bool hi = half != 0;
 #pragma unroll 4
   for (int i = 0; i < n; ++i) {
     const uint32_t a = __ldg(fb + i) + shift_row;
-    const uint4 v = __ldg(lm128 + (a >> 4) + half);
+    // a row none of whose 16 cells can still reach the keep threshold stops loading (see the row test below)
+    const uint4 v = alive ? __ldg(lm128 + (a >> 4) + half) : make_uint4(0u, 0u, 0u, 0u);
     uint32_t w0, w1, w2;
     if (K == 0) {
       const uint32_t p2 = __shfl_xor_sync(0xffffffffu, v.z, 1);
@@ -739,7 +745,7 @@ __global__ void __launch_bounds__(256, 4) k_refine(RefineParams p) {
   const int total = p.off[p.n_work];
   const LevelDev low = p.lv[p.L - 1];
   const int row = lane >> 1, half = lane & 1;
-  unsigned long long feats_done = 0, feats_read = 0;
+  unsigned feats_done = 0, rows_read = 0;  // per warp: a few candidates x (features x 16 rows)
   lm_record* __restrict__ out = reinterpret_cast<lm_record*>(p.hdr + 1);
   if (p.bp_clear)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.bp_words; i += gridDim.x * blockDim.x) p.bp_clear[i] = 0u;
@@ -813,13 +819,17 @@ __global__ void __launch_bounds__(256, 4) k_refine(RefineParams p) {
         // row start (which decides who trades what) is constant over a whole group of features.
         const uint4* __restrict__ lm128 = reinterpret_cast<const uint4*>(lv.lm);
         const uint32_t shift_row = (uint32_t)(cy * lv.Wd + cx + row * lv.Wd);
-        // Early exit (exact): a candidate only produces output if its best cell reaches raw_keep.  Every
-        // remaining feature adds at most 4 to any cell, so once max(cells so far) + 4 * remaining falls
-        // short the candidate is dropped (LL.cpp:1935-1937) whatever the rest adds -- stop reading.
+        // Early exit (exact), per patch row: a candidate only produces output if its best cell reaches raw_keep.
+        // Every remaining feature adds at most 4 to any cell, so a ROW whose best cell so far + 4 * remaining
+        // falls short can never hold the best cell of a kept candidate: its lane pair stops loading (its stale
+        // sums stay below raw_keep, so they can neither win nor tie).  When no row is left the candidate is
+        // dropped (LL.cpp:1935-1937) whatever the rest adds.  Tested every LM_REFINE_CHECK features.
         int nf_level = 0;
         for (int m = 0; m < p.M; ++m) nf_level += p.tslot[(size_t)g * p.S + l * p.M + m].y;
         const int raw_keep = lm_min_kept_raw(p.threshold, nf_level);
-        int done = 0;
+        int done = 0, since = 0;
+        bool alive = true;
+        unsigned rows_alive = 16;
         feats_done += nf_level;  // the reference's work for this candidate (algorithmic bytes / 256)
         for (int m = 0; m < p.M && !pruned; ++m) {
           const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
@@ -833,33 +843,39 @@ __global__ void __launch_bounds__(256, 4) k_refine(RefineParams p) {
             const uint32_t o = ((uint32_t)grp + shift_row) & 15u;
             const uint32_t sh = (o & 3u) << 3;
             while (n > 0) {
-              const int take = min(n, 63 - pend);
+              const int take = min(n, LM_REFINE_CHECK - pend);
               switch (o >> 2) {
-                case 0: refine_rows<0>(lm128, fb, take, shift_row, half, sh, a8, b8); break;
-                case 1: refine_rows<1>(lm128, fb, take, shift_row, half, sh, a8, b8); break;
-                case 2: refine_rows<2>(lm128, fb, take, shift_row, half, sh, a8, b8); break;
-                default: refine_rows<3>(lm128, fb, take, shift_row, half, sh, a8, b8); break;
+                case 0: refine_rows<0>(lm128, fb, take, shift_row, half, sh, alive, a8, b8); break;
+                case 1: refine_rows<1>(lm128, fb, take, shift_row, half, sh, alive, a8, b8); break;
+                case 2: refine_rows<2>(lm128, fb, take, shift_row, half, sh, alive, a8, b8); break;
+                default: refine_rows<3>(lm128, fb, take, shift_row, half, sh, alive, a8, b8); break;
               }
               fb += take;
               n -= take;
               pend += take;
               done += take;
-              if (pend == 63) {  // 63 * 4 = 252: no carry between packed bytes
+              since += take;
+              if (pend == LM_REFINE_CHECK) {  // <= 63: 63 * 4 = 252, no carry between packed bytes
                 s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
                 s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
                 a8 = b8 = 0;
                 pend = 0;
                 uint32_t mx = max(max(max(s01 & 0xFFFF, s01 >> 16), max(s23 & 0xFFFF, s23 >> 16)),
                                   max(max(s45 & 0xFFFF, s45 >> 16), max(s67 & 0xFFFF, s67 >> 16)));
-                mx = __reduce_max_sync(0xffffffffu, mx);
-                if ((int)mx + 4 * (nf_level - done) < raw_keep) { pruned = true; break; }
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));  // the row's 16 cells
+                rows_read += (unsigned)since * rows_alive;
+                since = 0;
+                alive = alive && ((int)mx + 4 * (nf_level - done) >= raw_keep);
+                const unsigned live = __ballot_sync(0xffffffffu, alive);
+                rows_alive = (unsigned)__popc(live) >> 1;
+                if (live == 0u) { pruned = true; break; }
               }
             }
           }
           s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
           s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
         }
-        feats_read += done;
+        rows_read += (unsigned)since * rows_alive;
         nf2 = nf_level;
       } else
       for (int m = 0; m < p.M; ++m) {
@@ -879,7 +895,7 @@ __global__ void __launch_bounds__(256, 4) k_refine(RefineParams p) {
           a8 += __funnelshift_r(w0, w1, sh);
           b8 += __funnelshift_r(w1, w2, sh);
           ++feats_done;
-          ++feats_read;
+          rows_read += 16;
           if (++pend == 63) {
             s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
             s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
@@ -924,8 +940,8 @@ __global__ void __launch_bounds__(256, 4) k_refine(RefineParams p) {
     }
   }
   if (lane == 0 && feats_done) {
-    atomicAdd(p.counters + 0, feats_done);
-    atomicAdd(p.counters + 1, feats_read);
+    atomicAdd(p.counters + 0, (unsigned long long)feats_done);
+    atomicAdd(p.counters + 1, (unsigned long long)rows_read);
   }
   if (p.px) {
     __syncthreads();
