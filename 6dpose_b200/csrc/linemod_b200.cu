@@ -765,9 +765,9 @@ static cudaError_t launch_coarse_bits(const BitScanParams& bp, bool smem, size_t
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    return launch_pdl(k_coarse_bits<R, true>, dim3(grid), dim3(512), smem_bytes, st, bp);
+    return launch_pdl(k_coarse_bits<R, true>, dim3(grid), dim3(LM_BITS_THREADS), smem_bytes, st, bp);
   }
-  return launch_pdl(k_coarse_bits<R, false>, dim3(grid), dim3(512), 0, st, bp);
+  return launch_pdl(k_coarse_bits<R, false>, dim3(grid), dim3(LM_BITS_THREADS), 0, st, bp);
 }
 
 // Enqueue every GPU stage of one frame on the detector's stream; no host synchronisation.
@@ -847,7 +847,8 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       bp.mask = d->d_mask; bp.raw = d->d_raw; bp.cnt = d->d_cnt;
       const size_t smem_bytes = (size_t)bp.bp_words * 4;
       const bool smem = smem_bytes <= LM_BITS_SMEM_LIMIT;
-      const int grid = std::min(d->sm_count, (d->n_items_bits + 15) / 16);
+      const int wpc = LM_BITS_THREADS / 32;
+      const int grid = std::min(d->sm_count, (d->n_items_bits + wpc - 1) / wpc);
       cudaError_t e = cudaSuccess;
       switch (low.rounds) {
         case 1: e = launch_coarse_bits<1>(bp, smem, smem_bytes, grid, st); break;
