@@ -2,7 +2,7 @@
 //
 // Reference being replaced: linemodLevelup::Detector::match and everything below it
 // (linemodLevelup/linemodLevelup.cpp of meiqua/6DPose @ 619be57, "LL.cpp"):
-//   kernels (lm_kernels.cuh): k_linear_memories, k_coarse_bits / k_coarse_bytes, k_scan_counts, k_refine
+//   kernels (lm_kernels.cuh): k_linear_memories, k_coarse_packed / k_coarse_bytes, k_scan_counts, k_refine
 //   lm_finish (host)   <- std::sort + std::unique                       LL.cpp:1772-1774
 // Integer results (raw scores, x, y, template ids) are bit-exact; the float similarity is produced by
 // the same two IEEE operations as the reference ((raw * 100.f) / (4 * n)).
@@ -541,6 +541,9 @@ static int prepare_work(lm_detector* d) {
     CU(cudaMalloc(&d->d_cnt, sizeof(int32_t) * d->cnt_elems));
     CU(cudaMalloc(&d->d_off, sizeof(int32_t) * d->cnt_elems));
   }
+  // per-template candidate counts are accumulated with atomics and re-zeroed by k_scan_counts
+  CU(cudaMemsetAsync(d->d_cnt, 0, sizeof(int32_t) * d->cnt_elems, d->stream));
+  CU(cudaStreamSynchronize(d->stream));
   // algorithmic bytes of the coarse scan for this shard: sum features x positions
   const int low = (d->L - 1) * d->M;
   int64_t bytes = 0;
@@ -756,19 +759,6 @@ static LevelDev level_dev(const LevelHost& h) {
   return v;
 }
 
-template <int R>
-static cudaError_t launch_coarse_bits(const BitScanParams& bp, bool smem, size_t smem_bytes, int grid, cudaStream_t st) {
-  if (smem) {
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_coarse_bits<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_BITS_SMEM_LIMIT + 4096);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
-    return launch_pdl(k_coarse_bits<R, true>, dim3(grid), dim3(LM_BITS_THREADS), smem_bytes, st, bp);
-  }
-  return launch_pdl(k_coarse_bits<R, false>, dim3(grid), dim3(LM_BITS_THREADS), 0, st, bp);
-}
 
 // Enqueue every GPU stage of one frame on the detector's stream; no host synchronisation.
 static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
@@ -847,17 +837,23 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       bp.mask = d->d_mask; bp.raw = d->d_raw; bp.cnt = d->d_cnt;
       const size_t smem_bytes = (size_t)bp.bp_words * 4;
       const bool smem = smem_bytes <= LM_BITS_SMEM_LIMIT;
-      const int wpc = LM_BITS_THREADS / 32;
-      const int grid = std::min(d->sm_count, (d->n_items_bits + wpc - 1) / wpc);
+      const int wpc = LM_PACK_THREADS / 32;
+      // tasks of 32 (template, word) entries; a few more CTAs than strictly needed keep every warp at one task
+      const long long tasks = (long long)d->n_items_bits * (low.nwords / 32) +
+                              ((long long)d->n_items_bits * (low.nwords % 32) + 31) / 32;
+      const int grid = (int)std::max<long long>(1, std::min<long long>(d->sm_count, (tasks + wpc - 1) / wpc));
       cudaError_t e = cudaSuccess;
-      switch (low.rounds) {
-        case 1: e = launch_coarse_bits<1>(bp, smem, smem_bytes, grid, st); break;
-        case 2: e = launch_coarse_bits<2>(bp, smem, smem_bytes, grid, st); break;
-        case 3: e = launch_coarse_bits<3>(bp, smem, smem_bytes, grid, st); break;
-        case 4: e = launch_coarse_bits<4>(bp, smem, smem_bytes, grid, st); break;
-        default: e = launch_coarse_bits<5>(bp, smem, smem_bytes, grid, st); break;
+      if (smem) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          e = cudaFuncSetAttribute(k_coarse_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_BITS_SMEM_LIMIT + 4096);
+          attr_set = e == cudaSuccess;
+        }
+        if (e == cudaSuccess) e = launch_pdl(k_coarse_packed<true>, dim3(grid), dim3(LM_PACK_THREADS), smem_bytes, st, bp);
+      } else {
+        e = launch_pdl(k_coarse_packed<false>, dim3(grid), dim3(LM_PACK_THREADS), 0, st, bp);
       }
-      if (e != cudaSuccess) return fail(LM_E_CUDA, "k_coarse_bits launch failed: %s", cudaGetErrorString(e));
+      if (e != cudaSuccess) return fail(LM_E_CUDA, "k_coarse_packed launch failed: %s", cudaGetErrorString(e));
       ++d->launches;
     }
     if (d->n_items_bytes > 0) {
@@ -874,7 +870,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[2], st));
-    CU(launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, (const int32_t*)d->d_cnt, d->d_off, n_work,
+    CU(launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, d->d_cnt, d->d_off, n_work,
                   px.world > 0 ? px_block : d->d_res, (int)(px.world > 0 ? d->px_cap : d->res_cap), d->shard_index,
                   d->d_counters));
     ++d->launches;

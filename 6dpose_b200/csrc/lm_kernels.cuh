@@ -2,7 +2,7 @@
 //
 // Reference functions replaced (linemodLevelup/linemodLevelup.cpp of meiqua/6DPose @ 619be57, "LL.cpp"):
 //   k_linear_memories  <- spread + computeResponseMaps + linearize          LL.cpp:1094-1243
-//   k_coarse_bits      <- similarity(_64) + addSimilarities(_64) + threshold loop (bit-sliced)
+//   k_coarse_packed    <- similarity(_64) + addSimilarities(_64) + threshold loop (bit-sliced)
 //   k_coarse_bytes     <- the same, byte-wise (templates the bit-sliced kernel does not take)
 //                                                                           LL.cpp:1284-1354, 1435-1534, 1836-1852
 //   k_scan_counts      <- candidates.push_back ordering (deterministic offsets)
@@ -309,139 +309,100 @@ __device__ __forceinline__ void vc_add8(uint32_t (&c)[8], const uint32_t (&x)[8]
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// One template, RR rounds of 32 position words (RR <= the level's rounds: positions at or beyond
-// template_positions P are zero by definition, so templates with P <= 1024 * RR need no more).
-template <int RR>
-__device__ __forceinline__ int coarse_bits_template(const BitScanParams& p, const uint32_t* __restrict__ bp, int lane, int w, int g,
-                                                    int nfeat, int P) {
-  constexpr int R = RR;
-    uint32_t ch[R][8], cn[R][8];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int b = 0; b < 8; ++b) ch[r][b] = cn[r][b] = 0u;
-
-    for (int m = 0; m < p.M; ++m) {
-      const TSlot ts = p.tslot[(size_t)g * p.S + p.slot_low + m];
-      const uint2* __restrict__ fd = p.fdesc + ts.x;
-      for (int f0 = 0; f0 < ts.y; f0 += 8) {
-        uint32_t xh[R][8], xn[R][8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          uint2 d = make_uint2(0u, LM_SKIP_BIT);
-          if (f0 + u < ts.y) d = __ldg(fd + f0 + u);
-          if (d.y & LM_SKIP_BIT) {  // warp-uniform
-#pragma unroll
-            for (int r = 0; r < R; ++r) xh[r][u] = xn[r][u] = 0u;
-          } else {
-            const int o = (d.y >> 8) & 7;
-            const uint32_t s = d.y & 31u;
-            const uint32_t* __restrict__ ph = bp + d.x + lane;
-            const uint32_t* __restrict__ pm = ph + (((o + 7) & 7) - o) * p.lbw;
-            const uint32_t* __restrict__ pp = ph + (((o + 1) & 7) - o) * p.lbw;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              const uint32_t h = __funnelshift_r(ph[32 * r], ph[32 * r + 1], s);
-              const uint32_t a = __funnelshift_r(pm[32 * r], pm[32 * r + 1], s);
-              const uint32_t b = __funnelshift_r(pp[32 * r], pp[32 * r + 1], s);
-              xh[r][u] = h;
-              xn[r][u] = (a | b) & ~h;
-            }
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          vc_add8(ch[r], xh[r]);
-          vc_add8(cn[r], xn[r]);
-        }
-      }
-    }
-
-    // score = 4*CH + CN (bit-sliced ripple add), positions >= P are zero (LL.cpp:1314), compare with
-    // the smallest passing raw score, emit the pass mask and the raw scores of the passing positions
-    const int raw_min = lm_min_passing_raw(p.threshold, nfeat);
-    int my_count = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int idx = lane + 32 * r;
-      if (idx < p.nwords) {
-        const int j0 = idx * 32;
-        uint32_t live = 0xffffffffu;   // positions < P carry a score
-        uint32_t valid = 0xffffffffu;  // positions < plane exist
-        if (P - j0 < 32) live = (P - j0 <= 0) ? 0u : (0xffffffffu >> (32 - (P - j0)));
-        if (p.plane - j0 < 32) valid = 0xffffffffu >> (32 - (p.plane - j0));
-        uint32_t s[11];
-        s[0] = cn[r][0] & live;
-        s[1] = cn[r][1] & live;
-        uint32_t carry = 0u;
-#pragma unroll
-        for (int b = 2; b < 10; ++b) {
-          const uint32_t a = (b < 8) ? cn[r][b] : 0u;
-          const uint32_t h = ch[r][b - 2];
-          s[b] = (a ^ h ^ carry) & live;
-          carry = (a & h) | (carry & (a ^ h));
-        }
-        s[10] = carry & live;
-        uint32_t pass;
-        if (raw_min > 2047) {
-          pass = 0u;
-        } else {
-          uint32_t gt = 0u, eq = 0xffffffffu;
-#pragma unroll
-          for (int b = 10; b >= 0; --b) {
-            if ((raw_min >> b) & 1) {
-              eq &= s[b];
-            } else {
-              gt |= eq & s[b];
-              eq &= ~s[b];
-            }
-          }
-          pass = (gt | eq) & valid;
-        }
-        p.mask[(size_t)w * p.nwords + idx] = pass;
-        my_count += __popc(pass);
-        while (pass) {
-          const int b = __ffs(pass) - 1;
-          pass &= pass - 1;
-          uint32_t v = 0;
-#pragma unroll
-          for (int k = 0; k < 11; ++k) v |= ((s[k] >> b) & 1u) << k;
-          p.raw[(size_t)w * p.plane + j0 + b] = (uint16_t)v;
-        }
-      }
-    }
-    // words beyond the rounds computed: every position is >= P, i.e. raw 0 (passes only if 0 does)
-    for (int idx = lane + 32 * R; idx < p.nwords; idx += 32) {
-      const int j0 = idx * 32;
-      uint32_t pass = 0u;
-      if (raw_min == 0) {
-        pass = (p.plane - j0 < 32) ? (0xffffffffu >> (32 - (p.plane - j0))) : 0xffffffffu;
-        for (int b = 0; b < 32; ++b)
-          if ((pass >> b) & 1u) p.raw[(size_t)w * p.plane + j0 + b] = 0;
-      }
-      p.mask[(size_t)w * p.nwords + idx] = pass;
-      my_count += __popc(pass);
-    }
-    return my_count;
-}
-
-// 24 warps per CTA: the default workload gives every CTA 21 templates, one per warp in a single round
-// (16 warps: 60 us, 20: 61 us, 24: 47 us; 80 registers, 24 bytes of spill)
-#ifndef LM_BITS_THREADS
-#define LM_BITS_THREADS 768
+#ifndef LM_PACK_THREADS
+#define LM_PACK_THREADS 768
 #endif
 
-template <int R, bool kSmem>
-__global__ void __launch_bounds__(LM_BITS_THREADS, 1) k_coarse_bits(BitScanParams p) {
+// K2 work decomposition.  A template only has ceil(P / 32) position words that can hold a score (P = its
+// template_positions, LL.cpp:1309; 33 of the 38 words of the level for the bench bank).  Giving a warp a
+// whole template in rounds of 32 words leaves 31 of 32 lanes idle in the last round, so the words of a
+// template are split in two kinds of tasks:
+//   * FULL rounds (32 consecutive words of one template): the feature descriptors are warp-uniform, so the
+//     plane addressing lives in the uniform datapath -- 15 instructions per feature;
+//   * the REMAINDERS (P/32 mod 32 words per template) of all templates of the CTA, laid end to end and cut
+//     into tasks of 32 entries: lane k owns one (template, word) and walks its own template's descriptors
+//     (lanes of 2-3 templates share a warp; 26 instructions per feature, but 32 busy lanes).
+// Both kinds sit in one dynamic queue per CTA (full rounds first).  Either way a lane owns ONE word: two 8-bit
+// vertical counters (H and N planes), the bit-sliced score 4*CH + CN, threshold compare and pass mask.
+#define LM_PACK_CHUNK 512  // templates whose task offsets are tabulated in shared memory at a time
+
+// score = 4*CH + CN (bit-sliced ripple add), positions >= P are zero (LL.cpp:1314), compare with the
+// smallest passing raw score, emit the pass mask and the raw scores of the passing positions
+__device__ __forceinline__ void coarse_emit(const BitScanParams& p, int w, int idx, int P, int nfeat, int words,
+                                            const uint32_t (&ch)[8], const uint32_t (&cn)[8]) {
+  const int raw_min = lm_min_passing_raw(p.threshold, nfeat);
+  const int j0 = idx * 32;
+  uint32_t live = 0xffffffffu;   // positions < P carry a score
+  uint32_t valid = 0xffffffffu;  // positions < plane exist
+  if (P - j0 < 32) live = (P - j0 <= 0) ? 0u : (0xffffffffu >> (32 - (P - j0)));
+  if (p.plane - j0 < 32) valid = 0xffffffffu >> (32 - (p.plane - j0));
+  uint32_t sc[11];
+  sc[0] = cn[0] & live;
+  sc[1] = cn[1] & live;
+  uint32_t carry = 0u;
+#pragma unroll
+  for (int b = 2; b < 10; ++b) {
+    const uint32_t a = (b < 8) ? cn[b] : 0u;
+    const uint32_t h = ch[b - 2];
+    sc[b] = (a ^ h ^ carry) & live;
+    carry = (a & h) | (carry & (a ^ h));
+  }
+  sc[10] = carry & live;
+  uint32_t pass;
+  if (raw_min > 2047) {
+    pass = 0u;
+  } else {
+    uint32_t gt = 0u, eq = 0xffffffffu;
+#pragma unroll
+    for (int b = 10; b >= 0; --b) {
+      if ((raw_min >> b) & 1) {
+        eq &= sc[b];
+      } else {
+        gt |= eq & sc[b];
+        eq &= ~sc[b];
+      }
+    }
+    pass = (gt | eq) & valid;
+  }
+  p.mask[(size_t)w * p.nwords + idx] = pass;
+  int my_count = __popc(pass);
+  while (pass) {
+    const int b = __ffs(pass) - 1;
+    pass &= pass - 1;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) v |= ((sc[k] >> b) & 1u) << k;
+    p.raw[(size_t)w * p.plane + j0 + b] = (uint16_t)v;
+  }
+  if (idx == words - 1) {
+    // words beyond the useful ones: every position is >= P, i.e. raw 0 (passes only if 0 does)
+    for (int x = words; x < p.nwords; ++x) {
+      const int q0 = x * 32;
+      uint32_t ps = 0u;
+      if (raw_min == 0) {
+        ps = (p.plane - q0 < 32) ? (0xffffffffu >> (32 - (p.plane - q0))) : 0xffffffffu;
+        for (int b = 0; b < 32; ++b)
+          if ((ps >> b) & 1u) p.raw[(size_t)w * p.plane + q0 + b] = 0;
+      }
+      p.mask[(size_t)w * p.nwords + x] = ps;
+      my_count += __popc(ps);
+    }
+  }
+  if (my_count) atomicAdd(p.cnt + w, my_count);  // zero before the frame (k_scan_counts re-zeroes)
+}
+
+template <bool kSmem>
+__global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanParams p) {
   lm_pdl_wait();
   extern __shared__ __align__(128) uint32_t s_bp[];
   __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_full[LM_PACK_CHUNK + 1];  // full rounds before template i
+  __shared__ int s_rem[LM_PACK_CHUNK + 1];   // remainder words before template i
+  __shared__ int s_warp[33];
   __shared__ int s_next;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  // this CTA's slice of the work items; warps pull from it dynamically
   const int t0 = (int)(((long long)p.n_items * blockIdx.x) / gridDim.x);
   const int t1 = (int)(((long long)p.n_items * (blockIdx.x + 1)) / gridDim.x);
-  if (threadIdx.x == 0) s_next = t0 + nwarps;
 
   const uint32_t* __restrict__ bp = p.bp;
   if (kSmem) {
@@ -465,7 +426,160 @@ __global__ void __launch_bounds__(LM_BITS_THREADS, 1) k_coarse_bits(BitScanParam
         done += n;
       }
     }
-    // everyone waits for phase 0 of the barrier
+    bp = s_bp;
+  }
+
+  bool staged = !kSmem;
+  for (int c0 = t0; c0 < t1; c0 += LM_PACK_CHUNK) {
+    const int nt = min(LM_PACK_CHUNK, t1 - c0);
+    // task offsets of the chunk's templates (while the bit-planes are still in flight the first time)
+    {
+      const int per = (nt + blockDim.x - 1) / blockDim.x;
+      const int b = min((int)threadIdx.x * per, nt), e = min(b + per, nt);
+      int sum_f = 0, sum_r = 0;
+      for (int i = b; i < e; ++i) {
+        const int g = p.work[p.items[c0 + i]];
+        const int words = min(max((p.tslot[(size_t)g * p.S + p.slot_low].z + 31) >> 5, 1), p.nwords);
+        sum_f += words >> 5;
+        sum_r += words & 31;
+      }
+      int tot_f, tot_r;
+      int run_f = block_exclusive_scan(sum_f, s_warp, &tot_f);
+      int run_r = block_exclusive_scan(sum_r, s_warp, &tot_r);
+      for (int i = b; i < e; ++i) {
+        const int g = p.work[p.items[c0 + i]];
+        const int words = min(max((p.tslot[(size_t)g * p.S + p.slot_low].z + 31) >> 5, 1), p.nwords);
+        s_full[i] = run_f;
+        s_rem[i] = run_r;
+        run_f += words >> 5;
+        run_r += words & 31;
+      }
+      if (threadIdx.x == 0) {
+        s_full[nt] = tot_f;
+        s_rem[nt] = tot_r;
+        s_next = nwarps;
+      }
+    }
+    __syncthreads();
+    if (!staged) {  // everyone waits for phase 0 of the barrier
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "WAIT_%=:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+          "@p bra DONE_%=;\n"
+          "bra WAIT_%=;\n"
+          "DONE_%=:\n"
+          "}\n" ::"r"(smem_u32(&s_bar))
+          : "memory");
+      staged = true;
+    }
+    const int n_full = s_full[nt], rem_words = s_rem[nt];
+    const int n_tasks = n_full + ((rem_words + 31) >> 5);
+    int task = warp;
+    while (task < n_tasks) {
+      if (task < n_full) {
+        // ---- a full round: 32 consecutive words of ONE template, warp-uniform descriptors ----
+        int lo = 0, hi = nt;  // last i with s_full[i] <= task
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_full[mid] <= task) lo = mid; else hi = mid;
+        }
+        const int r = task - s_full[lo];
+        const int w = p.items[c0 + lo];
+        const int g = p.work[w];
+        const int P = p.tslot[(size_t)g * p.S + p.slot_low].z;  // equal for all modalities (host checked)
+        const int words = min(max((P + 31) >> 5, 1), p.nwords);
+        const int idx = 32 * r + lane;
+        int nfeat = 0;
+        uint32_t ch[8], cn[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) ch[b] = cn[b] = 0u;
+        for (int m = 0; m < p.M; ++m) {
+          const TSlot ts = p.tslot[(size_t)g * p.S + p.slot_low + m];
+          nfeat += ts.y;
+          const uint2* __restrict__ fd = p.fdesc + ts.x;
+          for (int f0 = 0; f0 < ts.y; f0 += 8) {
+            uint32_t xh[8], xn[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              uint2 d = make_uint2(0u, LM_SKIP_BIT);
+              if (f0 + u < ts.y) d = __ldg(fd + f0 + u);
+              if (d.y & LM_SKIP_BIT) {  // warp-uniform
+                xh[u] = xn[u] = 0u;
+              } else {
+                const int o = (d.y >> 8) & 7;
+                const uint32_t sft = d.y & 31u;
+                const uint32_t* __restrict__ ph = bp + d.x + idx;
+                const uint32_t* __restrict__ pm = ph + (((o + 7) & 7) - o) * p.lbw;
+                const uint32_t* __restrict__ pp = ph + (((o + 1) & 7) - o) * p.lbw;
+                const uint32_t h = __funnelshift_r(ph[0], ph[1], sft);
+                const uint32_t a = __funnelshift_r(pm[0], pm[1], sft);
+                const uint32_t b = __funnelshift_r(pp[0], pp[1], sft);
+                xh[u] = h;
+                xn[u] = (a | b) & ~h;
+              }
+            }
+            vc_add8(ch, xh);
+            vc_add8(cn, xn);
+          }
+        }
+        coarse_emit(p, w, idx, P, nfeat, words, ch, cn);
+      } else {
+        // ---- remainders: lane k owns entry e of the chunk's remainder words ----
+        const int e = (task - n_full) * 32 + lane;
+        const bool active = e < rem_words;
+        const int ee = active ? e : rem_words - 1;
+        int lo = 0, hi = nt;  // last i with s_rem[i] <= ee
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_rem[mid] <= ee) lo = mid; else hi = mid;
+        }
+        const int w = p.items[c0 + lo];
+        const int g = p.work[w];
+        const int P = p.tslot[(size_t)g * p.S + p.slot_low].z;
+        const int words = min(max((P + 31) >> 5, 1), p.nwords);
+        const int idx = (words & ~31) + (ee - s_rem[lo]);  // behind the template's full rounds
+        int nfeat = 0;
+        uint32_t ch[8], cn[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) ch[b] = cn[b] = 0u;
+        for (int m = 0; m < p.M; ++m) {
+          const TSlot ts = p.tslot[(size_t)g * p.S + p.slot_low + m];
+          nfeat += ts.y;
+          const uint2* __restrict__ fd = p.fdesc + ts.x;
+          const int maxn = __reduce_max_sync(0xffffffffu, ts.y);
+          for (int f0 = 0; f0 < maxn; f0 += 8) {
+            uint32_t xh[8], xn[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              uint2 d = make_uint2(0u, LM_SKIP_BIT);
+              if (f0 + u < ts.y) d = __ldg(fd + f0 + u);
+              const bool skip = (d.y & LM_SKIP_BIT) != 0u;
+              const int o = (d.y >> 8) & 7;
+              const uint32_t sft = d.y & 31u;
+              const uint32_t* __restrict__ ph = bp + (skip ? 0u : d.x) + idx;
+              const uint32_t* __restrict__ pm = ph + (((o + 7) & 7) - o) * (skip ? 0 : p.lbw);
+              const uint32_t* __restrict__ pp = ph + (((o + 1) & 7) - o) * (skip ? 0 : p.lbw);
+              const uint32_t h = __funnelshift_r(ph[0], ph[1], sft);
+              const uint32_t a = __funnelshift_r(pm[0], pm[1], sft);
+              const uint32_t b = __funnelshift_r(pp[0], pp[1], sft);
+              xh[u] = skip ? 0u : h;
+              xn[u] = skip ? 0u : ((a | b) & ~h);
+            }
+            vc_add8(ch, xh);
+            vc_add8(cn, xn);
+          }
+        }
+        if (active) coarse_emit(p, w, idx, P, nfeat, words, ch, cn);
+      }
+      int nxt = 0;
+      if (lane == 0) nxt = atomicAdd(&s_next, 1);
+      task = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+    __syncthreads();  // the offset tables and s_next are rebuilt for the next chunk
+  }
+  if (kSmem && !staged) {  // a CTA without templates still has to see its copy land before it exits
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -474,35 +588,11 @@ __global__ void __launch_bounds__(LM_BITS_THREADS, 1) k_coarse_bits(BitScanParam
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(bar)
+        "}\n" ::"r"(smem_u32(&s_bar))
         : "memory");
-    bp = s_bp;
-  } else {
-    __syncthreads();
-  }
-
-  int it = t0 + warp;
-  while (it < t1) {
-    const int w = p.items[it];
-    const int g = p.work[w];
-    int nfeat = 0;
-    for (int m = 0; m < p.M; ++m) nfeat += p.tslot[(size_t)g * p.S + p.slot_low + m].y;
-    const int P = p.tslot[(size_t)g * p.S + p.slot_low].z;  // equal for all modalities (host checked)
-    const int need = max(1, (((P + 31) >> 5) + 31) >> 5);    // rounds that hold positions < P
-    int my_count;
-    if (R >= 2 && need == 1) my_count = coarse_bits_template<1>(p, bp, lane, w, g, nfeat, P);
-    else if (R >= 3 && need == 2) my_count = coarse_bits_template<(R >= 3 ? 2 : 1)>(p, bp, lane, w, g, nfeat, P);
-    else if (R >= 4 && need == 3) my_count = coarse_bits_template<(R >= 4 ? 3 : 1)>(p, bp, lane, w, g, nfeat, P);
-    else if (R >= 5 && need == 4) my_count = coarse_bits_template<(R >= 5 ? 4 : 1)>(p, bp, lane, w, g, nfeat, P);
-    else my_count = coarse_bits_template<R>(p, bp, lane, w, g, nfeat, P);
-    my_count = __reduce_add_sync(0xffffffffu, my_count);
-    if (lane == 0) p.cnt[w] = my_count;
-
-    int nxt = 0;
-    if (lane == 0) nxt = atomicAdd(&s_next, 1);
-    it = __shfl_sync(0xffffffffu, nxt, 0);
   }
 }
+
 
 // --------------------------------------------------------------------------------------------
 // K2 (byte-wise): same result for templates the bit-sliced kernel does not take (more than 255
@@ -609,7 +699,7 @@ __global__ void __launch_bounds__(1024) k_coarse_bytes(ByteScanParams p) {
 // --------------------------------------------------------------------------------------------
 // exclusive scan of the per-template candidate counts -> global candidate offsets (ordered)
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
+__global__ void __launch_bounds__(1024) k_scan_counts(int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
                                                      lm_result_header* __restrict__ hdr, int capacity, int shard,
                                                      unsigned long long* __restrict__ counters) {
   lm_pdl_wait();
@@ -623,6 +713,7 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
   for (int i = b; i < e; ++i) {
     off[i] = run;
     run += cnt[i];
+    cnt[i] = 0;  // k_coarse_packed accumulates the next frame's counts with atomics
   }
   if (threadIdx.x == 0) {
     off[n] = total;
