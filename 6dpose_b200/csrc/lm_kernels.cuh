@@ -835,7 +835,10 @@ __device__ __forceinline__ void refine_rows(const uint4* __restrict__ lm128, con
   }
 }
 
-__global__ void __launch_bounds__(256, 4) k_refine(RefineParams p) {
+#ifndef LM_REFINE_MIN_CTAS
+#define LM_REFINE_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(256, LM_REFINE_MIN_CTAS) k_refine(RefineParams p) {
   lm_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;

@@ -457,7 +457,7 @@ def main():
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         default_wl = (args.templates, args.features, args.width, args.height, args.threshold) == (3115, 150, 640, 480, 75.0)
-        key = "k_coarse_bits" if dominant == "k_coarse_scan" else dominant
+        key = "k_coarse_packed" if dominant == "k_coarse_scan" else dominant
         if world == 1 and default_wl and key in tr["kernels"]:
             traffic = tr["kernels"][key]["dram_bytes"]
             traffic_src = tr["source"]
