@@ -837,10 +837,14 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       bp.mask = d->d_mask; bp.raw = d->d_raw; bp.cnt = d->d_cnt;
       const size_t smem_bytes = (size_t)bp.bp_words * 4;
       const bool smem = smem_bytes <= LM_BITS_SMEM_LIMIT;
-      const int wpc = LM_PACK_THREADS / 32;
-      // tasks of 32 (template, word) entries; a few more CTAs than strictly needed keep every warp at one task
+      // tasks of 32 words (full rounds + packed remainders).  One task per warp and one round per CTA: the CTA
+      // size follows the shard (24 warps for the whole bench bank on one GPU, 4-8 warps for a 1/8 shard), so a
+      // small shard spreads over all SMs instead of filling a few, and leaves registers to the other frames in
+      // flight.
       const long long tasks = (long long)d->n_items_bits * (low.nwords / 32) +
                               ((long long)d->n_items_bits * (low.nwords % 32) + 31) / 32;
+      int wpc = (int)((tasks + d->sm_count - 1) / d->sm_count);
+      wpc = std::min(LM_PACK_THREADS / 32, std::max(4, (wpc + 3) & ~3));
       const int grid = (int)std::max<long long>(1, std::min<long long>(d->sm_count, (tasks + wpc - 1) / wpc));
       cudaError_t e = cudaSuccess;
       if (smem) {
@@ -849,9 +853,9 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
           e = cudaFuncSetAttribute(k_coarse_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_BITS_SMEM_LIMIT + 4096);
           attr_set = e == cudaSuccess;
         }
-        if (e == cudaSuccess) e = launch_pdl(k_coarse_packed<true>, dim3(grid), dim3(LM_PACK_THREADS), smem_bytes, st, bp);
+        if (e == cudaSuccess) e = launch_pdl(k_coarse_packed<true>, dim3(grid), dim3(wpc * 32), smem_bytes, st, bp);
       } else {
-        e = launch_pdl(k_coarse_packed<false>, dim3(grid), dim3(LM_PACK_THREADS), 0, st, bp);
+        e = launch_pdl(k_coarse_packed<false>, dim3(grid), dim3(wpc * 32), 0, st, bp);
       }
       if (e != cudaSuccess) return fail(LM_E_CUDA, "k_coarse_packed launch failed: %s", cudaGetErrorString(e));
       ++d->launches;
