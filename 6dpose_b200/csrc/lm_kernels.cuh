@@ -152,16 +152,23 @@ __global__ void __launch_bounds__(256) k_linear_memories(LinMemParams p) {
 // one (label, grid) plane are computed SIMD-in-register and written with one 32-bit store.  Needs
 // cols % 4 == 0 and Wd % 4 == 0 (every BASELINE size); other sizes use k_linear_memories above.
 // Bit-planes are OR-ed in with atomics (the caller zeroes them first).
-__global__ void __launch_bounds__(256) k_linear_memories_band(LinMemParams p) {
-  lm_pdl_wait();
-  extern __shared__ __align__(16) uint8_t s_band[];
-  int l = 0, first = 0;
-  while (l + 1 < p.L && (int)blockIdx.x >= p.lv[l].block_end) { first = p.lv[l].block_end; ++l; }
-  const LinMemLevel& lv = p.lv[l];
-  const int m = blockIdx.y;
-  const int bi = (int)blockIdx.x - first;
+// (row, column) of flat index i in a [rows][width] grid, advanced by `step` without a division
+struct RowCol {
+  int r, c;
+  __device__ __forceinline__ RowCol(int i, int width) : r(i / width), c(i - (i / width) * width) {}
+  __device__ __forceinline__ void advance(int step, int width) {
+    c += step;
+    while (c >= width) { c -= width; ++r; }
+  }
+};
+
+// TT = the level's sampling step at compile time (4 and 8 are the reference's defaults: window loops unroll and
+// the grid arithmetic is shifts), 0 = any T at run time.
+template <int TT>
+__device__ __forceinline__ void linear_memories_band_level(const LinMemLevel& lv, int m, int bi, uint8_t* s_band) {
+  const int T = TT > 0 ? TT : lv.T;
   const int py = bi / lv.nseg, seg = bi - py * lv.nseg;  // row of sampled positions, column segment
-  const int T = lv.T, cols = lv.cols, rows = lv.rows, Wd = lv.Wd;
+  const int cols = lv.cols, rows = lv.rows, Wd = lv.Wd;
   const int Wseg = Wd / lv.nseg;        // positions in this segment (multiple of 4)
   const int x0 = seg * Wseg * T;        // first image column of the segment
   const int cseg = Wseg * T;            // image columns that produce this segment's positions
@@ -173,54 +180,88 @@ __global__ void __launch_bounds__(256) k_linear_memories_band(LinMemParams p) {
   const uint8_t* __restrict__ q = (m == 0) ? lv.q[0] : lv.q[1];
   const int y0 = py * T;
   const int wpr = Wp >> 2, cw = cseg >> 2;
+  const int nthr = blockDim.x;
   // A: stage the input rows (zero beyond the image = clipping at the bottom/right edge)
-  for (int i = threadIdx.x; i < nin * wpr; i += blockDim.x) {
-    const int r = i / wpr, w = i - r * wpr;
-    uint32_t v = 0;
-    if (x0 + 4 * w < cols && y0 + r < rows) v = __ldg(reinterpret_cast<const uint32_t*>(q + (size_t)(y0 + r) * cols + x0) + w);
-    reinterpret_cast<uint32_t*>(s_in)[i] = v;
+  {
+    RowCol rc(threadIdx.x, wpr);
+    for (int i = threadIdx.x; i < nin * wpr; i += nthr, rc.advance(nthr, wpr)) {
+      uint32_t v = 0;
+      if (x0 + 4 * rc.c < cols && y0 + rc.r < rows)
+        v = __ldg(reinterpret_cast<const uint32_t*>(q + (size_t)(y0 + rc.r) * cols + x0) + rc.c);
+      reinterpret_cast<uint32_t*>(s_in)[i] = v;
+    }
   }
   __syncthreads();
   // B: horizontal OR over dx < T, 4 pixels at a time
-  for (int i = threadIdx.x; i < nin * cw; i += blockDim.x) {
-    const int r = i / cw, w = i - r * cw;
-    const uint32_t* row = reinterpret_cast<const uint32_t*>(s_in + r * Wp);
-    uint32_t acc = 0;
-    for (int dx = 0; dx < T; ++dx) {
-      const int b = 4 * w + dx;
-      acc |= __funnelshift_r(row[b >> 2], row[(b >> 2) + 1], (b & 3) << 3);
+  {
+    RowCol rc(threadIdx.x, cw);
+    for (int i = threadIdx.x; i < nin * cw; i += nthr, rc.advance(nthr, cw)) {
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(s_in + rc.r * Wp) + rc.c;
+      uint32_t acc = row[0];
+      if (TT == 4) {
+        const uint32_t n1 = row[1];
+        acc |= __funnelshift_r(row[0], n1, 8) | __funnelshift_r(row[0], n1, 16) | __funnelshift_r(row[0], n1, 24);
+      } else if (TT == 8) {
+        const uint32_t n1 = row[1], n2 = row[2];
+        acc |= __funnelshift_r(row[0], n1, 8) | __funnelshift_r(row[0], n1, 16) | __funnelshift_r(row[0], n1, 24) | n1 |
+               __funnelshift_r(n1, n2, 8) | __funnelshift_r(n1, n2, 16) | __funnelshift_r(n1, n2, 24);
+      } else {
+        for (int dx = 1; dx < T; ++dx) acc |= __funnelshift_r(row[dx >> 2], row[(dx >> 2) + 1], (dx & 3) << 3);
+      }
+      reinterpret_cast<uint32_t*>(s_h + rc.r * Wp)[rc.c] = acc;
     }
-    reinterpret_cast<uint32_t*>(s_h + r * Wp)[w] = acc;
   }
   __syncthreads();
   // C: vertical OR over dy < T
-  for (int i = threadIdx.x; i < T * cw; i += blockDim.x) {
-    const int r = i / cw, w = i - r * cw;
-    uint32_t acc = 0;
-    for (int dy = 0; dy < T; ++dy) acc |= reinterpret_cast<const uint32_t*>(s_h + (r + dy) * Wp)[w];
-    reinterpret_cast<uint32_t*>(s_sp + r * Wp)[w] = acc;
+  {
+    RowCol rc(threadIdx.x, cw);
+    for (int i = threadIdx.x; i < T * cw; i += nthr, rc.advance(nthr, cw)) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int dy = 0; dy < (TT > 0 ? TT : 1); ++dy) acc |= reinterpret_cast<const uint32_t*>(s_h + (rc.r + dy) * Wp)[rc.c];
+      if (TT == 0)
+        for (int dy = 1; dy < T; ++dy) acc |= reinterpret_cast<const uint32_t*>(s_h + (rc.r + dy) * Wp)[rc.c];
+      reinterpret_cast<uint32_t*>(s_sp + rc.r * Wp)[rc.c] = acc;
+    }
   }
   __syncthreads();
   // D: responses in linear-memory order, 4 positions per store
   const int T2 = T * T, q4 = Wseg >> 2;
   const int n = T2 * lv.plane;
   uint8_t* __restrict__ out = lv.lm + (size_t)m * lv.mod_stride;
-  for (int i = threadIdx.x; i < T2 * q4; i += blockDim.x) {
-    const int g = i / q4, k = i - g * q4;
-    const int gy = g / T, gx = g - gy * T;
+  const int pos_row = py * Wd + seg * Wseg;
+  RowCol gk(threadIdx.x, q4);  // r = grid g, c = group of 4 positions k
+  for (int i = threadIdx.x; i < T2 * q4; i += nthr, gk.advance(nthr, q4)) {
+    const int g = gk.r, k = gk.c;
+    const int gy = TT > 0 ? g / TT : g / T, gx = g - gy * T;
     const uint8_t* sp = s_sp + gy * Wp + (4 * k) * T + gx;
     const uint32_t V = (uint32_t)sp[0] | ((uint32_t)sp[T] << 8) | ((uint32_t)sp[2 * T] << 16) | ((uint32_t)sp[3 * T] << 24);
-    const int pos = g * lv.plane + py * Wd + seg * Wseg + 4 * k;  // multiple of 4
+    const int pos = g * lv.plane + pos_row + 4 * k;  // multiple of 4
+    uint8_t* __restrict__ o0 = out + pos;
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
       const uint32_t hit = (V >> o) & 0x01010101u;
       const uint32_t nb = ((V >> ((o + 1) & 7)) | (V >> ((o + 7) & 7))) & 0x01010101u;
-      *reinterpret_cast<uint32_t*>(out + (size_t)o * n + pos) = (hit << 2) | (nb & ~hit);
+      *reinterpret_cast<uint32_t*>(o0 + (size_t)o * n) = (hit << 2) | (nb & ~hit);
       if (lv.bp) {
         const uint32_t nib = ((hit * 0x01020408u) >> 24) & 0xFu;  // the 4 hit bits, position order
         if (nib) atomicOr(lv.bp + (size_t)(m * 8 + o) * lv.lbw + (pos >> 5), nib << (pos & 31));
       }
     }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_linear_memories_band(LinMemParams p) {
+  lm_pdl_wait();
+  extern __shared__ __align__(16) uint8_t s_band[];
+  int l = 0, first = 0;
+  while (l + 1 < p.L && (int)blockIdx.x >= p.lv[l].block_end) { first = p.lv[l].block_end; ++l; }
+  const LinMemLevel& lv = p.lv[l];
+  const int bi = (int)blockIdx.x - first;
+  switch (lv.T) {  // block-uniform
+    case 4: linear_memories_band_level<4>(lv, blockIdx.y, bi, s_band); break;
+    case 8: linear_memories_band_level<8>(lv, blockIdx.y, bi, s_band); break;
+    default: linear_memories_band_level<0>(lv, blockIdx.y, bi, s_band); break;
   }
 }
 

@@ -112,3 +112,42 @@ def test_reads_the_reference_fixture_banks():
     old = bk.TemplateBank()
     old.read_class(REF_CASE + "writeClasses/06_template.yaml", 2)   # older dialect with an extra depth: key
     assert old.num_templates() == 1
+
+
+def test_finish_orders_shuffled_records_and_validates_boxes():
+    """lm_finish = (work, seq) ordering (counting sort inside the library) + the reference's std::sort /
+    std::unique: any permutation of the same records gives the same matches; lm_set_boxes checks its input.
+    Host-only handle: no GPU involved."""
+    lib = importlib.import_module("6dpose_b200._lib")
+    synth = importlib.import_module("6dpose_b200.synth")
+    bank = synth.synth_bank(30, num_features=63, seed=9, class_ids=("01_template", "02_template"))
+    packed = bank.pack(bank.class_ids(), 4)
+    nat = lib.NativeDetector([4, 8], device=-1)
+    nat.load_bank(packed, 4)
+    nat.select(None, 0, 1)
+    rng = np.random.RandomState(3)
+    n = 4000
+    rec = np.zeros(n, lib.RECORD_DTYPE)
+    rec["work"] = rng.randint(0, 60, n)
+    rec["seq"] = rng.permutation(n)          # unique (work, seq) pairs
+    rec["x"] = rng.randint(0, 40, n) * 4
+    rec["y"] = rng.randint(0, 30, n) * 4
+    rec["similarity"] = (rng.randint(750, 1000, n) / 10.0).astype(np.float32)  # many ties
+    want = nat.finish(rec[np.lexsort((rec["seq"], rec["work"]))])
+    for _ in range(3):
+        got = nat.finish(rec[rng.permutation(n)])
+        assert got.tobytes() == want.tobytes()
+    assert len(want) <= n and np.all(np.diff(want["similarity"]) <= 0)
+    bad = rec.copy()
+    bad["work"][5] = 60                       # outside the selection
+    with pytest.raises(RuntimeError):
+        nat.finish(bad)
+    G = packed["tmeta"].shape[0]
+    nat.set_boxes(np.full((G, 2), 50, np.int32))
+    nat.set_boxes(None)
+    with pytest.raises(RuntimeError):
+        nat.set_boxes(np.full((G + 1, 2), 50, np.int32))
+    with pytest.raises(RuntimeError):
+        nat.set_boxes(np.full((G, 2), 40000, np.int32))
+    with pytest.raises(lib.LinemodLibraryError):   # GPU stages refuse on a host-only handle
+        nat.enqueue_post(0.5, 3)
