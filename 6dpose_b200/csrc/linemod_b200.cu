@@ -792,15 +792,21 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
         const LevelHost& lv = d->lv[l];
         band = band && (lv.cols % 4 == 0) && (lv.Wd % 4 == 0) && (lv.plane % 4 == 0);
         // column segments: as many as keep a multiple of 4 positions per segment (more CTAs in flight)
+        // the most segments (a divisor of Wd / 4, so that a segment keeps a multiple of 4 positions) that still
+        // leave every thread of the CTA one 4-position group of one grid: equal, light CTAs on every level
         int nseg = 1;
-        while (nseg < 8 && lv.Wd % (nseg * 2 * 4) == 0 && (lv.T * lv.T * lv.Wd) / (nseg * 2 * 4) >= 128) nseg *= 2;
+        if (lv.Wd % 4 == 0)
+          for (int k = 1; k <= 16 && k <= lv.Wd / 4; ++k)
+            if ((lv.Wd / 4) % k == 0 && (lv.T * lv.T * (lv.Wd / 4)) / k >= 128) nseg = k;
         p.lv[l].nseg = nseg;
         const size_t wp = (size_t)((lv.Wd / nseg * lv.T + lv.T + 3 + 4) & ~3);
         smem = std::max(smem, wp * (size_t)(2 * (2 * lv.T - 1) + lv.T));
       }
       band = band && smem <= 160 * 1024;
       int blocks = 0;
-      for (int l = 0; l < d->L; ++l) {
+      // block index order = lowest level first: its CTAs are the heavy ones (T*T = 64 grids per position row plus
+      // the bit-plane atomics), started last they would be the tail of the launch
+      for (int l = d->L - 1; l >= 0; --l) {
         const LevelHost& lv = d->lv[l];
         LinMemLevel& q = p.lv[l];
         for (int m = 0; m < d->M; ++m) q.q[m] = lv.q_src[m];

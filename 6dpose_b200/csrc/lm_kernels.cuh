@@ -113,8 +113,9 @@ __device__ __forceinline__ uint32_t spread_window(const uint8_t* __restrict__ q,
 __global__ void __launch_bounds__(256) k_linear_memories(LinMemParams p) {
   lm_pdl_wait();
   // which level does this block serve (<= 4 levels: linear search over the uniform block index)
-  int l = 0, first = 0;
-  while (l + 1 < p.L && (int)blockIdx.x >= p.lv[l].block_end) { first = p.lv[l].block_end; ++l; }
+  // which level does this block serve: blocks are numbered lowest level first (<= 4 levels: linear search)
+  int l = p.L - 1, first = 0;
+  while (l > 0 && (int)blockIdx.x >= p.lv[l].block_end) { first = p.lv[l].block_end; --l; }
   const LinMemLevel& lv = p.lv[l];
   const int m = blockIdx.y;
   const int n = lv.T * lv.T * lv.plane;
@@ -254,8 +255,9 @@ __device__ __forceinline__ void linear_memories_band_level(const LinMemLevel& lv
 __global__ void __launch_bounds__(256) k_linear_memories_band(LinMemParams p) {
   lm_pdl_wait();
   extern __shared__ __align__(16) uint8_t s_band[];
-  int l = 0, first = 0;
-  while (l + 1 < p.L && (int)blockIdx.x >= p.lv[l].block_end) { first = p.lv[l].block_end; ++l; }
+  // which level does this block serve: blocks are numbered lowest level first (<= 4 levels: linear search)
+  int l = p.L - 1, first = 0;
+  while (l > 0 && (int)blockIdx.x >= p.lv[l].block_end) { first = p.lv[l].block_end; --l; }
   const LinMemLevel& lv = p.lv[l];
   const int bi = (int)blockIdx.x - first;
   switch (lv.T) {  // block-uniform
