@@ -832,6 +832,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     }
     if (d->timing) CU(cudaEventRecord(d->ev[1], st));
     // K2
+    bool scan_fused = false;
     if (d->n_items_bits > 0) {
       BitScanParams bp;
       bp.bp = low.d_bp; bp.bp_words = (uint32_t)((size_t)d->M * 8 * low.lbw);
@@ -841,6 +842,15 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       bp.S = d->S; bp.M = d->M; bp.slot_low = (d->L - 1) * d->M;
       bp.threshold = threshold;
       bp.mask = d->d_mask; bp.raw = d->d_raw; bp.cnt = d->d_cnt;
+      const bool fuse_scan = d->n_items_bytes == 0;
+      scan_fused = fuse_scan;
+      bp.off = fuse_scan ? d->d_off : nullptr;
+      bp.n_work = n_work;
+      bp.hdr = px.world > 0 ? px_block : d->d_res;
+      bp.capacity = (int)(px.world > 0 ? d->px_cap : d->res_cap);
+      bp.shard = d->shard_index;
+      bp.counters = d->d_counters;
+      bp.ticket = reinterpret_cast<int*>(d->d_counters + 3);
       const size_t smem_bytes = (size_t)bp.bp_words * 4;
       const bool smem = smem_bytes <= LM_BITS_SMEM_LIMIT;
       // tasks of 32 words (full rounds + packed remainders).  One task per warp and one round per CTA: the CTA
@@ -880,10 +890,12 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[2], st));
-    CU(launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, d->d_cnt, d->d_off, n_work,
-                  px.world > 0 ? px_block : d->d_res, (int)(px.world > 0 ? d->px_cap : d->res_cap), d->shard_index,
-                  d->d_counters));
-    ++d->launches;
+    if (!scan_fused) {
+      CU(launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, d->d_cnt, d->d_off, n_work,
+                    px.world > 0 ? px_block : d->d_res, (int)(px.world > 0 ? d->px_cap : d->res_cap), d->shard_index,
+                    d->d_counters));
+      ++d->launches;
+    }
     if (d->timing) CU(cudaEventRecord(d->ev[3], st));
   }
   if (refine_only) {

@@ -323,6 +323,14 @@ struct BitScanParams {
   uint32_t* mask;  // [n_work][nwords] pass bits, position order
   uint16_t* raw;   // [n_work][plane] raw score, written at passing positions only
   int32_t* cnt;    // [n_work]
+  // candidate-offset scan fused behind the scan (the last CTA to finish does what k_scan_counts does); off == null:
+  // a separate k_scan_counts launch follows (banks that also need k_coarse_bytes)
+  int32_t* off;
+  int n_work;
+  lm_result_header* hdr;
+  int capacity, shard;
+  unsigned long long* counters;
+  int* ticket;     // zero between launches
 };
 
 #define CSA(sum, carry, a, b, c)                 \
@@ -355,6 +363,41 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 #ifndef LM_PACK_THREADS
 #define LM_PACK_THREADS 768
 #endif
+
+// exclusive scan of the per-template candidate counts -> off[], result header and counters reset for k_refine,
+// counts re-zeroed for the next frame's atomics.  Whole CTA.
+__device__ __forceinline__ void scan_counts_block(int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
+                                                  lm_result_header* __restrict__ hdr, int capacity, int shard,
+                                                  unsigned long long* __restrict__ counters, int* s_warp) {
+  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int b = min((int)threadIdx.x * per, n), e = min(b + per, n);
+  int sum = 0;
+  for (int i = b; i < e; ++i) sum += __ldcg(cnt + i);
+  int total;
+  int run = block_exclusive_scan(sum, s_warp, &total);
+  for (int i = b; i < e; ++i) {
+    off[i] = run;
+    run += __ldcg(cnt + i);
+    cnt[i] = 0;  // k_coarse_packed accumulates the next frame's counts with atomics
+  }
+  if (threadIdx.x == 0) {
+    off[n] = total;
+    hdr->count = 0;  // k_refine appends kept records behind the header
+    hdr->coarse_candidates = total;
+    hdr->capacity = capacity;
+    hdr->shard = shard;
+    counters[0] = 0ull;  // k_refine accumulates into them
+    counters[1] = 0ull;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_counts(int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
+                                                     lm_result_header* __restrict__ hdr, int capacity, int shard,
+                                                     unsigned long long* __restrict__ counters) {
+  lm_pdl_wait();
+  __shared__ int s_warp[33];
+  scan_counts_block(cnt, off, n, hdr, capacity, shard, counters, s_warp);
+}
 
 // K2 work decomposition.  A template only has ceil(P / 32) position words that can hold a score (P = its
 // template_positions, LL.cpp:1309; 33 of the 38 words of the level for the bench bank).  Giving a warp a
@@ -622,6 +665,19 @@ __global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanPar
     }
     __syncthreads();  // the offset tables and s_next are rebuilt for the next chunk
   }
+  if (p.off) {
+    // the last CTA to get here owns the scan: every other CTA's masks / counts are fenced before its ticket
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      scan_counts_block(p.cnt, p.off, p.n_work, p.hdr, p.capacity, p.shard, p.counters, s_warp);
+      if (threadIdx.x == 0) *p.ticket = 0;
+    }
+  }
   if (kSmem && !staged) {  // a CTA without templates still has to see its copy land before it exits
     asm volatile(
         "{\n"
@@ -742,32 +798,6 @@ __global__ void __launch_bounds__(1024) k_coarse_bytes(ByteScanParams p) {
 // --------------------------------------------------------------------------------------------
 // exclusive scan of the per-template candidate counts -> global candidate offsets (ordered)
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_scan_counts(int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
-                                                     lm_result_header* __restrict__ hdr, int capacity, int shard,
-                                                     unsigned long long* __restrict__ counters) {
-  lm_pdl_wait();
-  __shared__ int s_warp[33];
-  const int per = (n + blockDim.x - 1) / blockDim.x;
-  const int b = threadIdx.x * per, e = min(b + per, n);
-  int sum = 0;
-  for (int i = b; i < e; ++i) sum += cnt[i];
-  int total;
-  int run = block_exclusive_scan(sum, s_warp, &total);
-  for (int i = b; i < e; ++i) {
-    off[i] = run;
-    run += cnt[i];
-    cnt[i] = 0;  // k_coarse_packed accumulates the next frame's counts with atomics
-  }
-  if (threadIdx.x == 0) {
-    off[n] = total;
-    hdr->count = 0;  // k_refine appends kept records behind the header
-    hdr->coarse_candidates = total;
-    hdr->capacity = capacity;
-    hdr->shard = shard;
-    counters[0] = 0ull;  // k_refine accumulates into them
-    counters[1] = 0ull;
-  }
-}
 
 // --------------------------------------------------------------------------------------------
 // K3: local refinement, one warp per coarse candidate, all upper pyramid levels

@@ -471,7 +471,9 @@ def main():
         "kernels": {
             "k_linear_memories": {"us": stage["linear_memories"]},
             "k_coarse_scan": {"us": scan_us, "alg_bytes": counters["scan_bytes"], "gbs": scan_gbs, "frac": scan_gbs / hbm},
-            "k_scan_counts": {"us": stage["offsets"]},
+            "k_scan_counts": {"us": stage["offsets"],
+                              "note": "the offset scan runs in the last CTA of the coarse scan (inside k_coarse_scan.us) "
+                                      "unless the bank needs k_coarse_bytes; this is the gap between the two events"},
             "k_refine": {"us": refine_us, "alg_bytes": counters["refine_bytes"], "gbs": refine_gbs, "frac": refine_gbs / hbm},
             "stages_total_us": stage["total"],
         },
