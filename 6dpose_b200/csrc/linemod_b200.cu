@@ -136,6 +136,7 @@ struct lm_detector {
   std::vector<int> class_of;            // template -> class (lm_finish), rebuilt when the bank changes
   std::vector<int32_t> order_cnt;       // order_records scratch
   std::vector<lm_record> order_tmp, finish_rec;
+  std::vector<uint8_t> finish_keys;
 
   // post-match stage (lm_post.cuh): greedy NMS on the device, top-k survivors to the host
   std::vector<int32_t> boxes;           // [G][2] caller's box sizes (empty: L0 template width/height)
@@ -1268,10 +1269,7 @@ struct HostMatch {  // LL.h:225-258 with class_index standing in for the class_i
   int x, y;
   float similarity;
   int class_index, template_id;
-  bool operator<(const HostMatch& o) const {
-    if (similarity != o.similarity) return similarity > o.similarity;
-    return template_id < o.template_id;
-  }
+  // operator< (similarity descending, then template_id ascending) lives in lm_finish's 64-bit sort keys
   bool operator==(const HostMatch& o) const {
     return x == o.x && y == o.y && similarity == o.similarity && class_index == o.class_index;
   }
@@ -1286,27 +1284,61 @@ extern "C" int lm_finish(lm_detector* d, const lm_record* records, int64_t n, lm
       for (int g = d->class_begin[c]; g < d->class_begin[c + 1]; ++g) d->class_of[(size_t)g] = c;
   }
   const std::vector<int>& class_of = d->class_of;
-  std::vector<lm_record>& rec = d->finish_rec;
-  rec.assign(records, records + n);
-  order_records(d, rec.data(), n);  // class order -> template_id -> coarse cell (LL.cpp:1797-1939)
-  std::vector<HostMatch> v;
-  v.reserve((size_t)n);
+  // (work, seq) order = class order -> template_id -> coarse cell, the order in which the reference's loops insert
+  // the matches (LL.cpp:1797-1939); callers that fetched the records through lm_fetch_records pass them sorted
+  const lm_record* rec = records;
+  if (!std::is_sorted(records, records + n, record_order)) {
+    d->finish_rec.assign(records, records + n);
+    order_records(d, d->finish_rec.data(), n);
+    rec = d->finish_rec.data();
+  }
+  // std::sort(matches) with Match::operator< (similarity descending, then template_id ascending; LL.h:233-240,
+  // LL.cpp:1772) on 16-byte keys: the comparator induces the same strict weak order on the same input sequence, so
+  // libstdc++'s introsort takes the same decisions and leaves the same permutation (ties included) as it would on
+  // the Match structs -- with one integer compare per step instead of a float and an int compare.
+  struct SortKey {
+    uint64_t key;  // ~order(similarity) : 32 | template_id : 32
+    uint32_t idx;
+    uint32_t pad;
+    bool operator<(const SortKey& o) const { return key < o.key; }
+  };
+  static thread_local std::vector<HostMatch> v;  // scratch, reused between calls
+  v.resize((size_t)n);
+  std::vector<uint8_t>& keybuf = d->finish_keys;
+  keybuf.resize(sizeof(SortKey) * (size_t)std::max<int64_t>(n, 1));
+  SortKey* keys = reinterpret_cast<SortKey*>(keybuf.data());
   for (int64_t i = 0; i < n; ++i) {
     const lm_record& r = rec[i];
     if (r.work < 0 || (size_t)r.work >= d->sel.size())
       return fail(LM_E_INVALID, "record %lld: work index %d out of range", (long long)i, r.work);
     const int g = d->sel[r.work];
     const int c = class_of[g];
-    v.push_back(HostMatch{r.x, r.y, r.similarity, c, g - d->class_begin[c]});
+    const int tid = g - d->class_begin[c];
+    v[(size_t)i] = HostMatch{r.x, r.y, r.similarity, c, tid};
+    uint32_t b;
+    memcpy(&b, &r.similarity, 4);
+    if ((b << 1) == 0u) b = 0u;                                       // -0.0f == 0.0f for operator<
+    const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // monotone in the float value
+    keys[i].key = ((uint64_t)(~ord) << 32) | (uint32_t)tid;           // descending similarity, ascending template_id
+    keys[i].idx = (uint32_t)i;
+    keys[i].pad = 0;
   }
-  std::sort(v.begin(), v.end());                      // LL.cpp:1772
-  v.erase(std::unique(v.begin(), v.end()), v.end());  // LL.cpp:1773-1774
-  *n_out = (int64_t)v.size();
-  if ((int64_t)v.size() > cap) return fail(LM_E_CAPACITY, "%zu matches, capacity %lld", v.size(), (long long)cap);
-  for (size_t i = 0; i < v.size(); ++i) {
-    out[i].x = v[i].x; out[i].y = v[i].y; out[i].similarity = v[i].similarity;
-    out[i].class_index = v[i].class_index; out[i].template_id = v[i].template_id;
+  std::sort(keys, keys + n);  // LL.cpp:1772
+  // std::unique (LL.cpp:1773-1774): drop an element equal (x, y, similarity, class) to the last one KEPT
+  int64_t m = 0;
+  int64_t last = -1;
+  for (int64_t i = 0; i < n; ++i) {
+    const HostMatch& h = v[keys[i].idx];
+    if (last >= 0 && v[(size_t)last] == h) continue;
+    last = keys[i].idx;
+    if (m < cap) {
+      out[m].x = h.x; out[m].y = h.y; out[m].similarity = h.similarity;
+      out[m].class_index = h.class_index; out[m].template_id = h.template_id;
+    }
+    ++m;
   }
+  *n_out = m;
+  if (m > cap) return fail(LM_E_CAPACITY, "%lld matches, capacity %lld", (long long)m, (long long)cap);
   return LM_OK;
 }
 
