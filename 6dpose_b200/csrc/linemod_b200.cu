@@ -88,6 +88,11 @@ struct LevelHost {
 struct lm_detector {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // host uploads: the upper-level label images travel on a second stream while the lowest level's linear
+  // memories and the coarse scan already run (they only need the lowest level)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_upper = nullptr;
+  bool upper_pending = false;
   int L = 0, M = LM_MAX_MODALITIES;
   int T[LM_MAX_LEVELS] = {0};
   LevelHost lv[LM_MAX_LEVELS];
@@ -214,6 +219,9 @@ extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** o
   CU(cudaGetDeviceProperties(&prop, device));
   d->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&d->ev_upper, cudaEventDisableTiming));
   CU(cudaMalloc(&d->d_counters, 4 * sizeof(unsigned long long)));
   CU(cudaMemset(d->d_counters, 0, 4 * sizeof(unsigned long long)));
   CU(cudaMallocHost(&d->h_counters, 4 * sizeof(unsigned long long)));
@@ -257,6 +265,9 @@ extern "C" void lm_destroy(lm_detector* d) {
   }
   cudaFree(d->fe_depth); cudaFree(d->fe_nraw);
   for (cudaEvent_t e : d->tev) cudaEventDestroy(e);
+  if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
+  if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+  if (d->ev_upper) cudaEventDestroy(d->ev_upper);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
 }
@@ -628,16 +639,32 @@ static int upload_quantized(lm_detector* d, const uint8_t* const* quantized, con
   if (rc) return rc;
   rc = size_levels(d, rows, cols, true);
   if (rc) return rc;
-  for (int l = 0; l < d->L; ++l) {
+  for (int i = 0; i < d->L * d->M; ++i)
+    if (!quantized[i]) return fail(LM_E_INVALID, "quantized[%d] is null", i);
+  // lowest level first, on the main stream: its linear memories and the coarse scan need nothing else.  The
+  // larger upper levels follow on the copy stream (ordered behind everything already enqueued) and are joined
+  // in front of the upper levels' linear memories (enqueue_stages).
+  const bool fork = d->L > 1;
+  if (fork) {
+    CU(cudaEventRecord(d->ev_fork, d->stream));
+    CU(cudaStreamWaitEvent(d->copy_stream, d->ev_fork, 0));
+  }
+  for (int l = d->L - 1; l >= 0; --l) {
     LevelHost& lv = d->lv[l];
+    cudaStream_t st = (fork && l < d->L - 1) ? d->copy_stream : d->stream;
     for (int m = 0; m < d->M; ++m) {
-      const uint8_t* src = quantized[l * d->M + m];
-      if (!src) return fail(LM_E_INVALID, "quantized[%d] is null", l * d->M + m);
-      CU(cudaMemcpyAsync(lv.d_q[m], src, (size_t)rows[l] * cols[l], cudaMemcpyHostToDevice, d->stream));
+      CU(cudaMemcpyAsync(lv.d_q[m], quantized[l * d->M + m], (size_t)rows[l] * cols[l], cudaMemcpyHostToDevice, st));
       lv.q_src[m] = lv.d_q[m];
     }
   }
-  if (sync) CU(cudaStreamSynchronize(d->stream));  // caller's buffers are only borrowed for the call
+  if (fork) {
+    CU(cudaEventRecord(d->ev_upper, d->copy_stream));
+    d->upper_pending = true;
+  }
+  if (sync) {  // caller's buffers are only borrowed for the call
+    CU(cudaStreamSynchronize(d->stream));
+    if (fork) CU(cudaStreamSynchronize(d->copy_stream));
+  }
   d->have_frame = true;
   d->have_run = false;
   return LM_OK;
@@ -656,6 +683,8 @@ extern "C" int lm_bind_quantized_device(lm_detector* d, const uint8_t* const* d_
       if (!d_quantized[l * d->M + m]) return fail(LM_E_INVALID, "d_quantized[%d] is null", l * d->M + m);
       d->lv[l].q_src[m] = d_quantized[l * d->M + m];
     }
+  if (d->upper_pending) CU(cudaStreamWaitEvent(d->stream, d->ev_upper, 0));  // an earlier upload nobody consumed
+  d->upper_pending = false;
   d->have_frame = true;
   d->have_run = false;
   return LM_OK;
@@ -677,6 +706,7 @@ extern "C" int lm_upload_images(lm_detector* d, const uint8_t* rgb, const uint16
   rc = size_levels(d, lrows, lcols, true);
   if (rc) return rc;
   cudaStream_t st = d->stream;
+  if (d->upper_pending) CU(cudaStreamWaitEvent(st, d->ev_upper, 0));  // an earlier upload nobody consumed
   if (!d->fe_lut) {
     // NORMAL_LUT[.][vy][vx] of normal_lut.i: 45-degree sector (offset by half a sector) of atan2(vy-10, vx-10);
     // the rule reproduces all 8000 entries of the reference table (tests/test_frontend.py)
@@ -747,6 +777,7 @@ extern "C" int lm_upload_images(lm_detector* d, const uint8_t* rgb, const uint16
   }
   CU(cudaStreamSynchronize(st));  // the caller's images are only borrowed for the call
   CU(cudaGetLastError());
+  d->upper_pending = false;
   d->have_frame = true;
   d->have_run = false;
   return LM_OK;
@@ -781,12 +812,16 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     d->ev = d->tev.data() + 5 * (size_t)(d->timing_runs % (int64_t)(d->tev.size() / 5));
     ++d->timing_runs;
   }
+  LinMemParams k1;
+  bool k1_band = false;
+  size_t k1_smem = 0;
+  int k1_blocks = 0, k1_done = 0;
   if (!refine_only) {
     if (d->timing) CU(cudaEventRecord(d->ev[0], st));
     // K1: one launch for every level and modality
     {
       LinMemParams p;
-      p.L = d->L; p.M = d->M;
+      p.L = d->L; p.M = d->M; p.block_offset = 0;
       bool band = true;
       size_t smem = 0;
       for (int l = 0; l < d->L; ++l) {
@@ -823,12 +858,19 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
           CU(cudaFuncSetAttribute(k_linear_memories_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
           attr_set = true;
         }
-        const LevelHost& low = d->lv[d->L - 1];
-        (void)low;  // bit-planes are OR-ed in: zero at allocation, re-zeroed by k_refine after every frame
-        CU(launch_pdl(k_linear_memories_band, dim3((unsigned)blocks, (unsigned)d->M), dim3(128), smem, st, p));
-      } else {
-        CU(launch_pdl(k_linear_memories, dim3((unsigned)blocks, (unsigned)d->M), dim3(256), 0, st, p));
       }
+      // bit-planes are OR-ed in: zero at allocation, re-zeroed by k_refine after every frame.
+      // With a host upload in flight (upper levels still on the copy stream) the launch is split: the lowest
+      // level now, the levels above it behind the coarse scan, once their images have landed.
+      k1 = p;
+      k1_band = band;
+      k1_smem = smem;
+      k1_blocks = blocks;
+      const int first_n = d->upper_pending ? p.lv[d->L - 1].block_end : blocks;
+      k1_done = first_n;
+      p.block_offset = 0;
+      if (band) CU(launch_pdl(k_linear_memories_band, dim3((unsigned)first_n, (unsigned)d->M), dim3(128), smem, st, p));
+      else CU(launch_pdl(k_linear_memories, dim3((unsigned)first_n, (unsigned)d->M), dim3(256), 0, st, p));
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[1], st));
@@ -898,6 +940,15 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[3], st));
+    if (k1_done < k1_blocks) {  // the upper levels' linear memories, behind their images
+      CU(cudaStreamWaitEvent(st, d->ev_upper, 0));
+      k1.block_offset = k1_done;
+      const unsigned nb = (unsigned)(k1_blocks - k1_done);
+      if (k1_band) CU(launch_pdl(k_linear_memories_band, dim3(nb, (unsigned)d->M), dim3(128), k1_smem, st, k1));
+      else CU(launch_pdl(k_linear_memories, dim3(nb, (unsigned)d->M), dim3(256), 0, st, k1));
+      ++d->launches;
+    }
+    d->upper_pending = false;
   }
   if (refine_only) {
     CU(cudaMemsetAsync(d->d_counters, 0, 2 * sizeof(unsigned long long), st));

@@ -86,6 +86,7 @@ struct LinMemLevel {
 struct LinMemParams {
   LinMemLevel lv[LM_MAX_LEVELS];
   int L, M;
+  int block_offset;  // added to blockIdx.x: a launch may cover only the lowest level, or only the levels above it
 };
 
 // OR of the forward TxT window at (x, y), clipped at the bottom/right image edge (LL.cpp:1094-1109).
@@ -114,14 +115,15 @@ __global__ void __launch_bounds__(256) k_linear_memories(LinMemParams p) {
   lm_pdl_wait();
   // which level does this block serve (<= 4 levels: linear search over the uniform block index)
   // which level does this block serve: blocks are numbered lowest level first (<= 4 levels: linear search)
+  const int bx = (int)blockIdx.x + p.block_offset;
   int l = p.L - 1, first = 0;
-  while (l > 0 && (int)blockIdx.x >= p.lv[l].block_end) { first = p.lv[l].block_end; --l; }
+  while (l > 0 && bx >= p.lv[l].block_end) { first = p.lv[l].block_end; --l; }
   const LinMemLevel& lv = p.lv[l];
   const int m = blockIdx.y;
   const int n = lv.T * lv.T * lv.plane;
   const uint8_t* __restrict__ q = (m == 0) ? lv.q[0] : lv.q[1];
   uint8_t* __restrict__ out = lv.lm + (size_t)m * lv.mod_stride;
-  const int i = ((int)blockIdx.x - first) * 256 + (int)threadIdx.x;  // 32-aligned across a warp
+  const int i = (bx - first) * 256 + (int)threadIdx.x;  // 32-aligned across a warp
   uint32_t v = 0;
   if (i < n) {
     const int g = i / lv.plane, pos = i - g * lv.plane;
@@ -256,10 +258,11 @@ __global__ void __launch_bounds__(256) k_linear_memories_band(LinMemParams p) {
   lm_pdl_wait();
   extern __shared__ __align__(16) uint8_t s_band[];
   // which level does this block serve: blocks are numbered lowest level first (<= 4 levels: linear search)
+  const int bx = (int)blockIdx.x + p.block_offset;
   int l = p.L - 1, first = 0;
-  while (l > 0 && (int)blockIdx.x >= p.lv[l].block_end) { first = p.lv[l].block_end; --l; }
+  while (l > 0 && bx >= p.lv[l].block_end) { first = p.lv[l].block_end; --l; }
   const LinMemLevel& lv = p.lv[l];
-  const int bi = (int)blockIdx.x - first;
+  const int bi = bx - first;
   switch (lv.T) {  // block-uniform
     case 4: linear_memories_band_level<4>(lv, blockIdx.y, bi, s_band); break;
     case 8: linear_memories_band_level<8>(lv, blockIdx.y, bi, s_band); break;
