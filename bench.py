@@ -174,6 +174,15 @@ def run_reference(args):
                          "arms": arms},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    try:  # poseRefine on the host: the numpy/scipy restatement (oracle/icp_oracle.py), one hypothesis
+        from oracle import icp_oracle
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "icp_case1.npz"))
+        x, y = [int(v) for v in gold["xy_scene_a"]]
+        t0 = time.perf_counter()
+        icp_oracle.pose_refine(gold["scene"], gold["model"], gold["K"], gold["K"], gold["R"], gold["t"].reshape(3), x, y)
+        out["icp_cpu"] = {"ms_per_hypothesis": (time.perf_counter() - t0) * 1e3, "kind": "port (numpy/scipy, 1 thread)"}
+    except Exception as e:
+        out["icp_cpu"] = {"error": repr(e)}
     emit(json.dumps(out))
 
 
@@ -516,6 +525,31 @@ def main():
         out["frontend"] = {"gpu_ms_per_frame": gpu_ms, "cv2_ms_per_frame": cv2_ms, "match_images_ms_per_frame": mi_ms,
                            "note": "lm_upload_images (H2D of raw RGB-D + 9 kernels + sync) vs 6dpose_b200/frontend.py (cv2); "
                                    "match_images = Detector::match from raw images through the C-ABI (lm_match_images)"}
+    if world == 1:
+        # poseRefine (BASELINE.json config 2): the drivers refine the first three NMS survivors; here as one batched
+        # call on the reference's own ICP fixture (tests/golden/icp_case1.npz = test/case1/pose/*), host buffers
+        try:
+            gold = np.load(os.path.join(ROOT, "tests", "golden", "icp_case1.npz"))
+            icp = lib.NativeIcp(local)
+            names = ("scene_a", "scene_b", "shift_0")
+            xy = [[int(v) for v in gold["xy_" + n_]] for n_ in names]
+            nh = len(names)
+            a = dict(scene_depth=gold["scene"], model_depths=[gold["model"]] * nh, sceneK=gold["K"],
+                     modelKs=np.stack([gold["K"]] * nh), Rs=np.stack([gold["R"]] * nh),
+                     ts=np.stack([gold["t"].reshape(3)] * nh), detect_xy=xy)
+            for _ in range(3):
+                icp.process_batch(**a)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                Ro, to, res = icp.process_batch(**a)
+            icp_ms = (time.perf_counter() - t0) / 20 * 1e3
+            st = icp.last_stats()
+            out["icp"] = {"hypotheses_per_call": nh, "ms_per_call": icp_ms, "hypotheses_per_s": nh / icp_ms * 1e3,
+                          "points": st["points"], "iterations_last": st["iterations"], "fitness": [float(r) for r in res],
+                          "note": "lm_icp_process_batch (host depth images in, poses out) on the reference's pose fixture; "
+                                  "parity vs the ICP oracle is held to 1e-4 in tests/test_gpu_icp.py (unpinned: Open3D)"}
+        except Exception as e:  # informative only
+            out["icp"] = {"error": repr(e)}
     if not args.no_cpu_baseline and world == 1:
         # the CPU arm runs in its own process (torch's bundled OpenMP runtime in this one throttles the oracle's
         # thread pool): same workload, same code path as `bench.py --impl reference`
@@ -527,6 +561,8 @@ def main():
         try:
             ref = json.loads(subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env).stdout.strip().split("\n")[-1])
             out["cpu_baseline"] = ref["cpu_baseline"]
+            if "icp_cpu" in ref and isinstance(out.get("icp"), dict):
+                out["icp"]["cpu_oracle"] = ref["icp_cpu"]
         except Exception as e:  # the baseline is informative; never lose the GPU line over it
             out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     emit(json.dumps(out))
