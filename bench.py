@@ -177,9 +177,9 @@ def run_reference(args):
     try:  # poseRefine on the host: the numpy/scipy restatement (oracle/icp_oracle.py), one hypothesis
         from oracle import icp_oracle
         gold = np.load(os.path.join(ROOT, "tests", "golden", "icp_case1.npz"))
-        x, y = [int(v) for v in gold["xy_scene_a"]]
+        x, y = [int(v) for v in gold["xy_shift_0"]]
         t0 = time.perf_counter()
-        icp_oracle.pose_refine(gold["scene"], gold["model"], gold["K"], gold["K"], gold["R"], gold["t"].reshape(3), x, y)
+        icp_oracle.pose_refine(gold["scene_shift_0"], gold["model"], gold["K"], gold["K"], gold["R"], gold["t"].reshape(3), x, y)
         out["icp_cpu"] = {"ms_per_hypothesis": (time.perf_counter() - t0) * 1e3, "kind": "port (numpy/scipy, 1 thread)"}
     except Exception as e:
         out["icp_cpu"] = {"error": repr(e)}
@@ -531,10 +531,9 @@ def main():
         try:
             gold = np.load(os.path.join(ROOT, "tests", "golden", "icp_case1.npz"))
             icp = lib.NativeIcp(local)
-            names = ("scene_a", "scene_b", "shift_0")
-            xy = [[int(v) for v in gold["xy_" + n_]] for n_ in names]
-            nh = len(names)
-            a = dict(scene_depth=gold["scene"], model_depths=[gold["model"]] * nh, sceneK=gold["K"],
+            nh = 3  # three hypotheses of the fixture's converging case (fitness 1, several Gauss-Newton iterations)
+            xy = [[int(v) for v in gold["xy_shift_0"]]] * nh
+            a = dict(scene_depth=gold["scene_shift_0"], model_depths=[gold["model"]] * nh, sceneK=gold["K"],
                      modelKs=np.stack([gold["K"]] * nh), Rs=np.stack([gold["R"]] * nh),
                      ts=np.stack([gold["t"].reshape(3)] * nh), detect_xy=xy)
             for _ in range(3):
