@@ -94,6 +94,33 @@ __device__ void smallest_eigenvector_3x3(double a00, double a01, double a02, dou
   else { n[0] = 0; n[1] = 0; n[2] = 1; }
 }
 
+// The clouds come out of voxel_down_sample sorted by voxel (x major), so index distance is spatial distance along
+// x: tiles are visited outwards from the CTA's own points, and a side is abandoned once the x gap alone puts every
+// remaining candidate beyond the current 30th neighbour of every thread (exact: a point of voxel column a has
+// x in [lo_a, lo_a + ICP_VOXEL)).  The kept set is the 30 smallest (distance, index) pairs in that order --
+// the same list a scan in index order with "first seen wins" produces -- so the normals do not depend on the
+// visiting order.
+#define ICP_VOXEL 0.0025
+
+__device__ __forceinline__ void knn_scan_tile(const double (*s_t)[3], int t0, int m, double px, double py, double pz,
+                                              double* bd, int* bi, int& have) {
+  for (int k = 0; k < m; ++k) {
+    const double dx = px - s_t[k][0], dy = py - s_t[k][1], dz = pz - s_t[k][2];
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    const int idx = t0 + k;
+    if (have < ICP_KNN || d2 < bd[have - 1] || (d2 == bd[have - 1] && idx < bi[have - 1])) {
+      int pos = have < ICP_KNN ? have++ : ICP_KNN - 1;
+      while (pos > 0 && (bd[pos - 1] > d2 || (bd[pos - 1] == d2 && bi[pos - 1] > idx))) {
+        bd[pos] = bd[pos - 1];
+        bi[pos] = bi[pos - 1];
+        --pos;
+      }
+      bd[pos] = d2;
+      bi[pos] = idx;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) k_icp_normals(const IcpJob* __restrict__ jobs, const double* __restrict__ pts,
                                                      double* __restrict__ normals) {
   __shared__ double s_t[ICP_TILE][3];
@@ -107,28 +134,39 @@ __global__ void __launch_bounds__(128) k_icp_normals(const IcpJob* __restrict__ 
   double bd[ICP_KNN];
   int bi[ICP_KNN];
   int have = 0;
-  for (int t0 = 0; t0 < n; t0 += ICP_TILE) {
-    __syncthreads();
-    for (int k = threadIdx.x; k < ICP_TILE * 3; k += blockDim.x) {
-      const int j = t0 + k / 3;
-      (&s_t[0][0])[k] = j < n ? P[(size_t)3 * t0 + k] : 0.0;
-    }
-    __syncthreads();
-    if (!live) continue;
-    const int m = min(ICP_TILE, n - t0);
-    for (int k = 0; k < m; ++k) {
-      const double dx = px - s_t[k][0], dy = py - s_t[k][1], dz = pz - s_t[k][2];
-      const double d2 = dx * dx + dy * dy + dz * dz;
-      if (have < ICP_KNN || d2 < bd[have - 1]) {
-        int pos = have < ICP_KNN ? have++ : ICP_KNN - 1;
-        while (pos > 0 && bd[pos - 1] > d2) {
-          bd[pos] = bd[pos - 1];
-          bi[pos] = bi[pos - 1];
-          --pos;
-        }
-        bd[pos] = d2;
-        bi[pos] = t0 + k;
+  const int ntiles = (n + ICP_TILE - 1) / ICP_TILE;
+  if (ntiles > 0) {
+    const int center = min((int)((blockIdx.x * blockDim.x + blockDim.x / 2) / ICP_TILE), ntiles - 1);
+    int lo = center - 1, hi = center + 1;
+    bool more_lo = lo >= 0, more_hi = hi < ntiles;
+    int tile = center;
+    for (;;) {
+      const int t0 = tile * ICP_TILE;
+      __syncthreads();
+      for (int k = threadIdx.x; k < ICP_TILE * 3; k += blockDim.x) {
+        const int j = t0 + k / 3;
+        (&s_t[0][0])[k] = j < n ? P[(size_t)3 * t0 + k] : 0.0;
       }
+      __syncthreads();
+      if (live) knn_scan_tile(s_t, t0, min(ICP_TILE, n - t0), px, py, pz, bd, bi, have);
+      // next tile: alternate sides while they are worth visiting (block-uniform decisions)
+      bool picked = false;
+      for (int side = 0; side < 2 && !picked; ++side) {
+        const bool up = ((tile >= center) == (side == 0)) ? false : true;  // prefer the side not just visited
+        if (up && more_hi) {
+          const double gap = P[(size_t)3 * hi * ICP_TILE] - ICP_VOXEL - px;  // every x beyond is > this
+          const bool useless = !live || (have == ICP_KNN && gap > 0.0 && gap * gap > bd[ICP_KNN - 1]);
+          if (__syncthreads_and(useless)) more_hi = false;
+          else { tile = hi++; more_hi = hi < ntiles; picked = true; }
+        } else if (!up && more_lo) {
+          const int last = min((lo + 1) * ICP_TILE, n) - 1;
+          const double gap = px - (P[(size_t)3 * last] + ICP_VOXEL);  // every x before is < that
+          const bool useless = !live || (have == ICP_KNN && gap > 0.0 && gap * gap > bd[ICP_KNN - 1]);
+          if (__syncthreads_and(useless)) more_lo = false;
+          else { tile = lo--; more_lo = lo >= 0; picked = true; }
+        }
+      }
+      if (!picked) break;
     }
   }
   if (!live) return;
