@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblinemod_b200.so")
 
 LM_OK, LM_E_INVALID, LM_E_CUDA, LM_E_STATE, LM_E_CAPACITY = 0, -1, -2, -3, -4
+SHARD_CONTIGUOUS, SHARD_INTERLEAVED = 0, 1
 
 MATCH_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("similarity", "<f4"), ("class_index", "<i4"), ("template_id", "<i4")])
 RECORD_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2"), ("similarity", "<f4"), ("work", "<i4"), ("seq", "<i4")])
@@ -21,7 +22,7 @@ HEADER_DTYPE = np.dtype([("count", "<i4"), ("coarse_candidates", "<i4"), ("capac
 PEER_HANDLE_BYTES = 64
 
 SYMBOLS = [
-    "lm_last_error", "lm_create", "lm_destroy", "lm_load_bank", "lm_select", "lm_shard_range",
+    "lm_last_error", "lm_create", "lm_destroy", "lm_load_bank", "lm_select", "lm_select_layout", "lm_shard_range", "lm_prepare",
     "lm_upload_quantized", "lm_upload_images", "lm_match_images", "lm_debug_quantized", "lm_bind_quantized_device", "lm_run", "lm_enqueue", "lm_complete", "lm_set_result_buffer", "lm_device_result", "lm_fetch_records",
     "lm_finish", "lm_match_quantized", "lm_debug_linear_memories", "lm_counters", "lm_set_timing",
     "lm_stage_times", "lm_stream", "lm_launch_count",
@@ -56,6 +57,8 @@ def load():
     L.lm_destroy.restype = None
     L.lm_load_bank.argtypes = [vp, c_int, i32p, c_int, i32p, i32p, c_i64]
     L.lm_select.argtypes = [vp, i32p, c_int, c_int, c_int]
+    L.lm_select_layout.argtypes = [vp, i32p, c_int, c_int, c_int, c_int]
+    L.lm_prepare.argtypes = [vp]
     L.lm_shard_range.argtypes = [vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
     L.lm_upload_quantized.argtypes = [vp, u8pp, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
     u8p_ = ctypes.POINTER(ctypes.c_uint8)
@@ -155,12 +158,16 @@ class NativeDetector:
         check(self._L.lm_load_bank(self._h, len(cb) - 1, self._i32(cb), int(slots), self._i32(tm), self._i32(ft),
                                    int(ft.shape[0])))
 
-    def select(self, class_indices=None, shard_index=0, shard_count=1):
+    def select(self, class_indices=None, shard_index=0, shard_count=1, layout=SHARD_CONTIGUOUS):
+        """layout: SHARD_CONTIGUOUS (blocks of the sequence) or SHARD_INTERLEAVED (rank r takes r, r+N, ...)."""
         if class_indices is None:
-            check(self._L.lm_select(self._h, None, -1, int(shard_index), int(shard_count)))
+            check(self._L.lm_select_layout(self._h, None, -1, int(shard_index), int(shard_count), int(layout)))
         else:
             a = np.ascontiguousarray(class_indices, np.int32)
-            check(self._L.lm_select(self._h, self._i32(a), int(a.shape[0]), int(shard_index), int(shard_count)))
+            check(self._L.lm_select_layout(self._h, self._i32(a), int(a.shape[0]), int(shard_index), int(shard_count), int(layout)))
+
+    def prepare(self):
+        check(self._L.lm_prepare(self._h))
 
     def shard_range(self):
         b, c = ctypes.c_int64(), ctypes.c_int64()

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -73,6 +74,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // --------------------------------------------------------------------------------------------
 #define LM_MAX_ROUNDS 5
 #define LM_BITS_SMEM_LIMIT (200 * 1024)
+#define LM_BAND_SMEM_LIMIT (160 * 1024)
 
 struct LevelHost {
   int T = 0, rows = 0, cols = 0, Wd = 0, Hd = 0, plane = 0;
@@ -118,8 +120,11 @@ struct lm_detector {
 
   // selection / shard
   std::vector<int32_t> sel;  // global template ids of the whole selected sequence
-  int64_t shard_begin = 0, shard_count = 0;
+  int64_t shard_begin = 0, shard_count = 0;  // contiguous layout: [begin, begin + count) of sel
   int shard_index = 0, shard_n = 1;
+  int shard_layout = LM_SHARD_CONTIGUOUS;
+  int64_t work_base = 0, work_stride = 1;    // entry w of the shard is sel[work_base + w * work_stride]
+  std::vector<int32_t> shard_sel;            // global template ids of this shard, in order
   int32_t* d_work = nullptr;
   int32_t* d_items_bits = nullptr; int n_items_bits = 0;    // work items per coarse kernel
   int32_t* d_items_bytes = nullptr; int n_items_bytes = 0;
@@ -149,7 +154,8 @@ struct lm_detector {
   lm_match* d_post_out = nullptr; lm_match* h_post_out = nullptr;  // LM_POST_MAX survivors
   int32_t* d_post_counts = nullptr; int32_t* h_post_counts = nullptr;
   uint8_t* d_post_live = nullptr; int64_t post_live_cap = 0;
-  bool post_pending = false;
+  bool post_pending = false, post_retry = false;
+  double post_iou = 0.5; int post_top_k = 0;
 
   // multi-GPU exchange fused into k_refine (lm_peer_*)
   uint8_t* px_buf = nullptr;            // this rank's exchange buffer (IPC-exportable cudaMalloc)
@@ -158,6 +164,7 @@ struct lm_detector {
   bool px_ipc = false;                  // peer bases opened with cudaIpcOpenMemHandle
   uint8_t* px_base[LM_MAX_PEERS] = {nullptr};
   int32_t px_seq = 0;
+  unsigned long long px_timeout_ns = 1000000000ull;  // collector gives up on a peer after 1 s (LINEMOD_B200_PEER_TIMEOUT_MS)
   PeerExchange* d_px = nullptr;         // device copy of the descriptor (static after connect)
   PeerExchange h_px;
 
@@ -218,6 +225,10 @@ extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** o
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   d->sm_count = prop.multiProcessorCount;
+  // function attributes are per DEVICE: every handle raises the dynamic shared-memory limits on its own device
+  // (a process may hold handles on several GPUs, e.g. lm_peer_connect_local across devices)
+  CU(cudaFuncSetAttribute(k_linear_memories_band, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_BAND_SMEM_LIMIT));
+  CU(cudaFuncSetAttribute(k_coarse_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_BITS_SMEM_LIMIT + 4096));
   CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
@@ -343,7 +354,13 @@ static int check_paths(const lm_detector* d, int g) {
 }
 
 extern "C" int lm_select(lm_detector* d, const int32_t* class_sel, int n_classes_sel, int shard_index, int shard_count) {
+  return lm_select_layout(d, class_sel, n_classes_sel, shard_index, shard_count, LM_SHARD_CONTIGUOUS);
+}
+
+extern "C" int lm_select_layout(lm_detector* d, const int32_t* class_sel, int n_classes_sel, int shard_index, int shard_count,
+                                int layout) {
   if (!d) return fail(LM_E_INVALID, "null detector");
+  if (layout != LM_SHARD_CONTIGUOUS && layout != LM_SHARD_INTERLEAVED) return fail(LM_E_INVALID, "unknown shard layout %d", layout);
   if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return fail(LM_E_INVALID, "bad shard %d/%d", shard_index, shard_count);
   std::vector<int32_t> sel;
   if (n_classes_sel < 0) {
@@ -376,8 +393,24 @@ extern "C" int lm_select(lm_detector* d, const int32_t* class_sel, int n_classes
   };
   d->shard_index = shard_index;
   d->shard_n = shard_count;
-  d->shard_begin = cut(shard_index);
-  d->shard_count = cut(shard_index + 1) - d->shard_begin;
+  d->shard_layout = layout;
+  if (layout == LM_SHARD_INTERLEAVED) {
+    // entry w of shard r is element r + w * N of the selected sequence: neighbouring templates (views / in-plane
+    // variants of one another, which pass or fail together) are dealt round the ranks, so the candidate load per
+    // rank evens out where contiguous blocks do not
+    d->work_base = shard_index;
+    d->work_stride = shard_count;
+    d->shard_begin = shard_index;
+    d->shard_count = ((int64_t)sel.size() - shard_index + shard_count - 1) / shard_count;
+    if (d->shard_count < 0) d->shard_count = 0;
+  } else {
+    d->shard_begin = cut(shard_index);
+    d->shard_count = cut(shard_index + 1) - d->shard_begin;
+    d->work_base = d->shard_begin;
+    d->work_stride = 1;
+  }
+  d->shard_sel.resize((size_t)d->shard_count);
+  for (int64_t w = 0; w < d->shard_count; ++w) d->shard_sel[(size_t)w] = sel[(size_t)(d->work_base + w * d->work_stride)];
   d->sel.swap(sel);  // after the cuts: the lambda reads `sel`
   d->work_dirty = true;
   d->post_dirty = true;
@@ -527,12 +560,12 @@ static int prepare_work(lm_detector* d) {
   cudaFree(d->d_work); d->d_work = nullptr;
   if (n > 0) {
     CU(cudaMalloc(&d->d_work, sizeof(int32_t) * (size_t)n));
-    CU(cudaMemcpyAsync(d->d_work, d->sel.data() + d->shard_begin, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, d->stream));
+    CU(cudaMemcpyAsync(d->d_work, d->shard_sel.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, d->stream));
     CU(cudaStreamSynchronize(d->stream));
   }
   {
     std::vector<int32_t> ib, iy;
-    for (int64_t i = 0; i < n; ++i) (d->bits_ok[d->sel[d->shard_begin + i]] ? ib : iy).push_back((int32_t)i);
+    for (int64_t i = 0; i < n; ++i) (d->bits_ok[d->shard_sel[(size_t)i]] ? ib : iy).push_back((int32_t)i);
     cudaFree(d->d_items_bits); d->d_items_bits = nullptr;
     cudaFree(d->d_items_bytes); d->d_items_bytes = nullptr;
     d->n_items_bits = (int)ib.size();
@@ -560,7 +593,7 @@ static int prepare_work(lm_detector* d) {
   const int low = (d->L - 1) * d->M;
   int64_t bytes = 0;
   for (int64_t i = 0; i < n; ++i) {
-    const int g = d->sel[d->shard_begin + i];
+    const int g = d->shard_sel[(size_t)i];
     for (int m = 0; m < d->M; ++m) {
       const TSlot& t = d->h_tslot[(size_t)g * d->S + low + m];
       if (t.z <= 0) continue;
@@ -838,7 +871,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
         const size_t wp = (size_t)((lv.Wd / nseg * lv.T + lv.T + 3 + 4) & ~3);
         smem = std::max(smem, wp * (size_t)(2 * (2 * lv.T - 1) + lv.T));
       }
-      band = band && smem <= 160 * 1024;
+      band = band && smem <= LM_BAND_SMEM_LIMIT;
       int blocks = 0;
       // block index order = lowest level first: its CTAs are the heavy ones (T*T = 64 grids per position row plus
       // the bit-plane atomics), started last they would be the tail of the launch
@@ -851,13 +884,6 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
         q.mod_stride = lv.mod_stride;
         blocks += band ? lv.Hd * q.nseg : (lv.T * lv.T * lv.plane + 255) / 256;
         q.block_end = blocks;
-      }
-      if (band) {
-        static bool attr_set = false;
-        if (!attr_set) {
-          CU(cudaFuncSetAttribute(k_linear_memories_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-          attr_set = true;
-        }
       }
       // bit-planes are OR-ed in: zero at allocation, re-zeroed by k_refine after every frame.
       // With a host upload in flight (upper levels still on the copy stream) the launch is split: the lowest
@@ -907,12 +933,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       const int grid = (int)std::max<long long>(1, std::min<long long>(d->sm_count, (tasks + wpc - 1) / wpc));
       cudaError_t e = cudaSuccess;
       if (smem) {
-        static bool attr_set = false;
-        if (!attr_set) {
-          e = cudaFuncSetAttribute(k_coarse_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_BITS_SMEM_LIMIT + 4096);
-          attr_set = e == cudaSuccess;
-        }
-        if (e == cudaSuccess) e = launch_pdl(k_coarse_packed<true>, dim3(grid), dim3(wpc * 32), smem_bytes, st, bp);
+        e = launch_pdl(k_coarse_packed<true>, dim3(grid), dim3(wpc * 32), smem_bytes, st, bp);
       } else {
         e = launch_pdl(k_coarse_packed<false>, dim3(grid), dim3(wpc * 32), 0, st, bp);
       }
@@ -961,7 +982,8 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     rp.tslot = d->d_tslot; rp.fbase = d->d_fbase; rp.fxy = d->d_fxy; rp.work = d->d_work;
     rp.off = d->d_off; rp.mask = d->d_mask; rp.raw = d->d_raw;
     rp.n_work = n_work; rp.nwords = low.nwords; rp.L = d->L; rp.S = d->S; rp.M = d->M;
-    rp.work_begin = (int)d->shard_begin;
+    rp.work_begin = (int)d->work_base;
+    rp.work_stride = (int)d->work_stride;
     rp.threshold = threshold;
     rp.hdr = d->d_res; rp.capacity = (int32_t)d->res_cap;
     rp.px = px.world > 0 ? d->d_px : nullptr;
@@ -982,7 +1004,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
   if (px.world > 0) {
     // collector: waits for all ranks' frame flags, packs the blocks into the ordinary result block
     CU(launch_pdl(k_peer_collect, dim3(1), dim3(1024), 0, st, px, d->px_seq, (int32_t)d->px_cap, d->d_res, (int32_t)d->res_cap,
-                  d->d_counters + 2));
+                  d->d_counters + 2, d->px_timeout_ns));
     ++d->launches;
   }
   if (d->timing) CU(cudaEventRecord(d->ev[4], st));
@@ -1043,6 +1065,33 @@ static int ensure_run_buffers(lm_detector* d) {
   return LM_OK;
 }
 
+// More kept records than slots in the internal result block: grow it and redo the refinement stage only (the coarse
+// outputs of the frame are still in place).  The header travels through a stack copy (the pinned staging block is
+// reallocated by ensure_run_buffers) with the new capacity patched in.
+static int grow_and_rerun(lm_detector* d) {
+  if (d->res_external)
+    return fail(LM_E_CAPACITY, "%d records kept, caller's result buffer holds %lld", d->h_res->count, (long long)d->res_cap);
+  if (d->px_rank >= 0) return fail(LM_E_CAPACITY, "%d records kept, the result block holds %lld", d->h_res->count, (long long)d->res_cap);
+  lm_result_header hdr = *d->h_res;
+  CU(cudaStreamSynchronize(d->stream));
+  cudaFree(d->d_res_own);
+  d->d_res_own = nullptr;
+  d->res_cap_own = (int64_t)hdr.count * 2;
+  CU(cudaMalloc(&d->d_res_own, sizeof(lm_result_header) + sizeof(lm_record) * (size_t)d->res_cap_own));
+  hdr.capacity = (int32_t)d->res_cap_own;
+  hdr.count = 0;
+  CU(cudaMemcpy(d->d_res_own, &hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+  int rc = ensure_run_buffers(d);
+  if (rc) return rc;
+  rc = enqueue_stages(d, d->last_threshold, true);
+  if (rc) return rc;
+  rc = enqueue_readback(d);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(d->stream));
+  CU(cudaGetLastError());
+  return LM_OK;
+}
+
 extern "C" int lm_enqueue(lm_detector* d, float threshold) {
   if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
   if (!d) return fail(LM_E_INVALID, "null detector");
@@ -1059,6 +1108,19 @@ extern "C" int lm_enqueue(lm_detector* d, float threshold) {
   return enqueue_stages(d, threshold, false);
 }
 
+extern "C" int lm_prepare(lm_detector* d) {
+  if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
+  if (!d) return fail(LM_E_INVALID, "null detector");
+  if (!d->have_frame) return fail(LM_E_STATE, "no frame uploaded (the frame size decides the feature addresses)");
+  if (d->S == 0) return fail(LM_E_STATE, "no template bank loaded");
+  CU(cudaSetDevice(d->device));
+  int rc = prepare_bank(d);
+  if (rc) return rc;
+  rc = prepare_work(d);
+  if (rc) return rc;
+  return ensure_run_buffers(d);
+}
+
 extern "C" int lm_complete(lm_detector* d) {
   if (d && d->device < 0) return fail(LM_E_STATE, "host-only handle (device -1): GPU stages are unavailable");
   if (!d) return fail(LM_E_INVALID, "null detector");
@@ -1068,28 +1130,16 @@ extern "C" int lm_complete(lm_detector* d) {
   CU(cudaStreamSynchronize(d->stream));
   CU(cudaGetLastError());
   if (d->px_rank >= 0) {
-    if (d->h_counters[2] == 1) return fail(LM_E_STATE, "peer exchange: a rank did not publish frame %d within the timeout", d->px_seq);
+    if (d->h_counters[2] == 1)
+      return fail(LM_E_STATE, "peer exchange: a rank did not publish frame %d within %llu ms (or an earlier frame already timed out "
+                  "on this device); disconnect and reconnect the exchange", d->px_seq, d->px_timeout_ns / 1000000ull);
     if (d->h_counters[2] == 2)
       return fail(LM_E_CAPACITY, "peer exchange: a shard kept more than %lld records (capacity given to lm_peer_export)",
                   (long long)d->px_cap);
   }
   if ((int64_t)d->h_res->count > d->res_cap) {
-    if (d->res_external)
-      return fail(LM_E_CAPACITY, "%d records kept, caller's result buffer holds %lld", d->h_res->count, (long long)d->res_cap);
-    // more kept records than slots: grow the internal block and redo the refinement stage only
-    cudaFree(d->d_res_own);
-    d->d_res_own = nullptr;
-    d->res_cap_own = (int64_t)d->h_res->count * 2;
-    CU(cudaMalloc(&d->d_res_own, sizeof(lm_result_header) + sizeof(lm_record) * (size_t)d->res_cap_own));
-    CU(cudaMemcpyAsync(d->d_res_own, d->h_res, sizeof(lm_result_header), cudaMemcpyHostToDevice, d->stream));
-    rc = ensure_run_buffers(d);
+    rc = grow_and_rerun(d);
     if (rc) return rc;
-    rc = enqueue_stages(d, d->last_threshold, true);
-    if (rc) return rc;
-    rc = enqueue_readback(d);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(d->stream));
-    CU(cudaGetLastError());
   }
   d->have_run = true;
   return LM_OK;
@@ -1139,6 +1189,13 @@ extern "C" int lm_peer_export(lm_detector* d, int world, int64_t capacity_record
   d->px_world = world;
   d->px_cap = capacity_records;
   d->px_seq = 0;
+  {
+    const int zero = 0;  // a fresh exchange starts with the device's abort flag down
+    CU(cudaMemcpyToSymbol(g_px_abort, &zero, sizeof(int)));
+    const char* ms = getenv("LINEMOD_B200_PEER_TIMEOUT_MS");
+    const long long v = ms ? atoll(ms) : 1000;
+    d->px_timeout_ns = (unsigned long long)(v < 1 ? 1 : (v > 600000 ? 600000 : v)) * 1000000ull;
+  }
   if (handle_out) {
     static_assert(sizeof(cudaIpcMemHandle_t) <= LM_PEER_HANDLE_BYTES, "IPC handle size");
     cudaIpcMemHandle_t h;
@@ -1464,7 +1521,6 @@ extern "C" int lm_enqueue_post(lm_detector* d, double iou_threshold, int top_k) 
   if (!d->d_res) return fail(LM_E_STATE, "no stages enqueued (call lm_enqueue first)");
   if (top_k > LM_POST_MAX) return fail(LM_E_INVALID, "top_k %d > %d", top_k, LM_POST_MAX);
   if (!(iou_threshold >= 0.0)) return fail(LM_E_INVALID, "IoU threshold must be >= 0");
-  if (d->sel.empty()) return fail(LM_E_STATE, "empty selection");
   CU(cudaSetDevice(d->device));
   int rc = prepare_post(d);
   if (rc) return rc;
@@ -1476,6 +1532,8 @@ extern "C" int lm_enqueue_post(lm_detector* d, double iou_threshold, int top_k) 
   p.out_counts = d->d_post_counts; p.live = d->d_post_live;
   CU(launch_pdl(k_post_nms, dim3(1), dim3(1024), 0, d->stream, p));
   ++d->launches;
+  d->post_iou = iou_threshold;
+  d->post_top_k = top_k;
   d->post_pending = true;
   return LM_OK;
 }
@@ -1494,13 +1552,27 @@ extern "C" int lm_complete_post(lm_detector* d, lm_match* out, int64_t cap, int6
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
   d->post_pending = false;
-  if (d->px_rank >= 0 && d->h_counters[2] == 1) return fail(LM_E_STATE, "peer exchange: a rank did not publish frame %d within the timeout", d->px_seq);
+  if (d->px_rank >= 0 && d->h_counters[2] == 1)
+    return fail(LM_E_STATE, "peer exchange: a rank did not publish frame %d within %llu ms", d->px_seq, d->px_timeout_ns / 1000000ull);
   if (d->px_rank >= 0 && d->h_counters[2] == 2) return fail(LM_E_CAPACITY, "peer exchange: a shard kept more than %lld records", (long long)d->px_cap);
   const int64_t n = d->h_post_counts[0];
   if (n_records) *n_records = d->h_post_counts[1];
-  if ((int64_t)d->h_post_counts[1] > d->res_cap)
-    return fail(LM_E_CAPACITY, "%d records kept, the result block holds %lld: the NMS did not see all of them", d->h_post_counts[1],
-                (long long)d->res_cap);
+  if ((int64_t)d->h_post_counts[1] > d->res_cap) {
+    // the NMS did not see every record: grow the block like lm_complete does, redo the refinement, run the NMS again
+    if (d->post_retry || d->res_external || d->px_rank >= 0)
+      return fail(LM_E_CAPACITY, "%d records kept, the result block holds %lld: the NMS did not see all of them", d->h_post_counts[1],
+                  (long long)d->res_cap);
+    CU(cudaMemcpyAsync(d->h_res, d->d_res, sizeof(lm_result_header), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int rc = grow_and_rerun(d);
+    if (rc) return rc;
+    rc = lm_enqueue_post(d, d->post_iou, d->post_top_k);
+    if (rc) return rc;
+    d->post_retry = true;
+    rc = lm_complete_post(d, out, cap, n_out, n_records);
+    d->post_retry = false;
+    return rc;
+  }
   *n_out = n;
   if (n > cap) return fail(LM_E_CAPACITY, "%lld survivors, capacity %lld", (long long)n, (long long)cap);
   if (n > first) {

@@ -859,7 +859,7 @@ struct RefineParams {
   const uint32_t* mask;  // [n_work][nwords]
   const uint16_t* raw;   // [n_work][plane_low]
   int n_work, nwords, L, S, M;
-  int work_begin;  // global offset of this shard in the selected sequence
+  int work_begin, work_stride;  // entry w of this shard is element work_begin + w * work_stride of the selected sequence
   float threshold;
   lm_result_header* hdr;  // result block: header, then `capacity` records
   int32_t capacity;
@@ -1108,7 +1108,7 @@ __global__ void __launch_bounds__(256, LM_REFINE_MIN_CTAS) k_refine(RefineParams
       if (slot < p.capacity) {
         lm_record r;
         r.x = (int16_t)x; r.y = (int16_t)y; r.similarity = sim;
-        r.work = p.work_begin + w;
+        r.work = p.work_begin + w * p.work_stride;
         r.seq = c;
         out[slot] = r;
         if (p.px) peer_store_record(p.px, p.px_seq, slot, *reinterpret_cast<const int4*>(&r));
@@ -1125,12 +1125,18 @@ __global__ void __launch_bounds__(256, LM_REFINE_MIN_CTAS) k_refine(RefineParams
   }
 }
 
+// Abort flag of the fused exchange, one per device (module-scope variable): the first collector that gives up on a peer
+// raises it and every later collector of ANY handle / lane on this device returns at once instead of spinning through
+// its own timeout -- one stalled rank costs one timeout, not lanes x frames of them.  Cleared by lm_peer_export.
+__device__ int g_px_abort = 0;
+
 // Collector of the fused exchange: waits until every rank's frame flag for `seq` has arrived in THIS rank's
 // buffer, then packs the `world` blocks of the frame slot into one ordinary result block (header.count =
-// all shards' kept records).  status: 0 ok, 1 a peer did not publish within the timeout, 2 a block
-// overflowed its capacity.  One CTA.
+// all shards' kept records).  status: 0 ok, 1 a peer did not publish within the timeout (or an earlier collector
+// on this device already gave up), 2 a block overflowed its capacity.  One CTA.
 __global__ void __launch_bounds__(1024) k_peer_collect(PeerExchange px, int32_t seq, int32_t block_capacity, lm_result_header* out_hdr,
-                                                       int32_t out_capacity, unsigned long long* status) {
+                                                       int32_t out_capacity, unsigned long long* status,
+                                                       unsigned long long timeout_ns) {
   lm_pdl_wait();
   __shared__ int s_cnt[LM_MAX_PEERS + 1];
   __shared__ int s_coarse[LM_MAX_PEERS];
@@ -1142,13 +1148,19 @@ __global__ void __launch_bounds__(1024) k_peer_collect(PeerExchange px, int32_t 
   if (tid < px.world) {
     const volatile int32_t* flag = reinterpret_cast<const volatile int32_t*>(mine + px.flags_offset) +
                                    (seq & 1) * LM_MAX_PEERS + tid;
+    const volatile int* abort_flag = &g_px_abort;
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     bool ok = true;
     while ((int32_t)(*flag - seq) < 0) {
+      if (*abort_flag) { ok = false; break; }
       __nanosleep(200);
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 20000000000ull) { ok = false; break; }  // 20 s: a peer never enqueued this frame
+      if (t1 - t0 > timeout_ns) {  // a peer never enqueued this frame (or died)
+        atomicExch(&g_px_abort, 1);
+        ok = false;
+        break;
+      }
     }
     __threadfence_system();  // acquire: the block contents were fenced before the flag
     const lm_result_header* h = reinterpret_cast<const lm_result_header*>(

@@ -52,6 +52,8 @@ __device__ __forceinline__ bool post_better(const PostKey& p, const PostKey& q) 
 }
 
 __global__ void __launch_bounds__(1024) k_post_nms(PostParams p) {
+  lm_pdl_wait();  // launched with programmatic stream serialization: the records / count of k_refine (k_peer_collect)
+                  // are only visible after this returns
   __shared__ PostKey s_best[32];
   __shared__ PostKey s_pick;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;

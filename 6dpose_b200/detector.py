@@ -68,6 +68,7 @@ class Detector:
         self._peers = None  # (rank, world) once dist.connect_peers has wired the fused exchange
         self.device = _default_device()
         self.shard = (0, 1)  # (index, count): template shard matched by this process (multi-GPU)
+        self.shard_layout = _lib.SHARD_CONTIGUOUS
         # quantization front-end used by match(): "gpu" (CUDA, lm_match_images) or "cv2" (host, frontend.py);
         # both produce the same label images (tests/test_gpu_frontend.py)
         self.frontend = os.environ.get("LINEMOD_B200_FRONTEND", "gpu")
@@ -130,11 +131,17 @@ class Detector:
         else:
             index = {c: i for i, c in enumerate(self._class_order)}
             sel = [index[c] for c in class_ids if c in index]  # unknown ids are skipped (LL.cpp:1765-1767)
-        key = (None if sel is None else tuple(sel), self.shard)
+        key = (None if sel is None else tuple(sel), self.shard, self.shard_layout)
         if key != self._selection:
-            nat.select(sel, self.shard[0], self.shard[1])
+            nat.select(sel, self.shard[0], self.shard[1], self.shard_layout)
             self._selection = key
         return nat
+
+    def _whole_bank_only(self, what):
+        # a detector left holding ONE template shard (dist.py) would silently return that shard's matches only
+        if self.shard[1] > 1 and self._peers is None:
+            raise RuntimeError("%s on a detector that holds template shard %d of %d without a connected peer exchange: "
+                               "use dist.match_quantized_sharded, or reset detector.shard = (0, 1)" % (what, self.shard[0], self.shard[1]))
 
     def quantize(self, sources, masks=None):
         """The host front-end: list over levels of [color_labels, normal_labels] (u8)."""
@@ -150,6 +157,7 @@ class Detector:
         if len(sources) != 2:
             raise RuntimeError("sources.size() == modalities.size()")  # CV_Assert LL.cpp:1707
         sources = [self._as_source(s, i) for i, s in enumerate(sources)]
+        self._whole_bank_only("match()")
         if self.frontend == "gpu" and self.shard[1] == 1:
             nat = self._select(list(class_ids))
             return self._to_matches(nat.match_images(sources[0], sources[1], list(masks), float(threshold)))
@@ -158,6 +166,7 @@ class Detector:
 
     def match_quantized(self, quantized, threshold, class_ids=()):
         """Same as match() but starting from quantized label images (the accelerated path proper)."""
+        self._whole_bank_only("match_quantized()")
         nat = self._select(list(class_ids))
         out = nat.match_quantized(quantized, float(threshold))
         return self._to_matches(out)
@@ -183,6 +192,7 @@ class Detector:
         """match + nms(dets, iou_threshold)[:top_k] of the reference's drivers (linemod_and_levelup_test.py:
         34-61, 325-350) in one call; the NMS runs on the GPU and only the survivors are copied back.
         Returns (list[Match] best first, number of raw matches before sort/unique)."""
+        self._whole_bank_only("match_top()")
         nat = self._select(list(class_ids))
         out, nrec = nat.match_top(quantized, float(threshold), float(iou_threshold), int(top_k))
         return self._to_matches(out), nrec

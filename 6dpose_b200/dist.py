@@ -68,6 +68,7 @@ def disconnect_peers(detector, group=None):
     dist.barrier(group=group)  # nobody may still be storing into a buffer that is about to be unmapped
     detector._native.peer_disconnect()
     detector._peers = None
+    detector.shard = (0, 1)
     dist.barrier(group=group)
 
 
@@ -76,12 +77,18 @@ def match_quantized_sharded(detector, quantized, threshold, class_ids=(), group=
     full, finished match list (identical to the single-GPU result)."""
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    connected = getattr(detector, "_peers", None) == (rank, world)
+    before = detector.shard
     detector.shard = shard_of(rank, world)
-    nat = detector._select(list(class_ids))
-    nat.upload_quantized(quantized)
-    nat.run(float(threshold))
-    if getattr(detector, "_peers", None) == (rank, world):
-        allrec = nat.fetch_records()  # fused exchange: the result block already holds every shard's records
-    else:
-        allrec = gather_records(nat.fetch_records(), group)
-    return detector._to_matches(nat.finish(allrec))
+    try:
+        nat = detector._select(list(class_ids))
+        nat.upload_quantized(quantized)
+        nat.run(float(threshold))
+        if connected:
+            allrec = nat.fetch_records()  # fused exchange: the result block already holds every shard's records
+        else:
+            allrec = gather_records(nat.fetch_records(), group)
+        return detector._to_matches(nat.finish(allrec))
+    finally:
+        if not connected:
+            detector.shard = before  # a later plain match() on this detector sees the whole bank again

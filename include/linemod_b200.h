@@ -83,7 +83,15 @@ int lm_load_bank(lm_detector* d, int n_classes, const int32_t* class_begin, int 
  * of that sequence (contiguous, balanced by features x positions) -- the multi-GPU template shard.
  * n_classes_sel < 0 selects all classes in bank order. */
 int lm_select(lm_detector* d, const int32_t* class_sel, int n_classes_sel, int shard_index, int shard_count);
-/* Global offset of this shard inside the selected sequence and its length. */
+/* Same with the shard layout chosen: LM_SHARD_CONTIGUOUS (lm_select's: one block of the sequence per shard) or
+ * LM_SHARD_INTERLEAVED (shard r takes elements r, r + N, r + 2N, ...: neighbouring templates -- views and in-plane
+ * variants that pass or fail together -- are dealt round the ranks, which evens out the candidate load).  Records
+ * carry the global index in the selected sequence either way, so lm_finish is unchanged. */
+#define LM_SHARD_CONTIGUOUS 0
+#define LM_SHARD_INTERLEAVED 1
+int lm_select_layout(lm_detector* d, const int32_t* class_sel, int n_classes_sel, int shard_index, int shard_count, int layout);
+/* Index of this shard's first element inside the selected sequence and the shard's length (contiguous layout: the
+ * shard is [begin, begin + count); interleaved: begin + k * shard_count, k < count). */
 int lm_shard_range(lm_detector* d, int64_t* begin, int64_t* count);
 
 /* Frame upload: quantized one-hot label images (output of QuantizedPyramid::quantize, LL.cpp:583-587,
@@ -112,6 +120,10 @@ int lm_run(lm_detector* d, float threshold);
  * buffer was too small for the number of coarse candidates. */
 int lm_enqueue(lm_detector* d, float threshold);
 int lm_complete(lm_detector* d);
+/* Everything lm_enqueue does lazily on a new bank / selection / frame size (feature addresses for the frame size,
+ * shard work lists, run buffers), done now: the first lm_enqueue afterwards only launches.  Needs a frame uploaded or
+ * bound (for its size).  SPMD callers use it so that no rank's first frame lags the others'. */
+int lm_prepare(lm_detector* d);
 
 /* Result block of the stages: by default an internal device buffer that grows on demand.  A caller
  * that wants the block in its own device memory (e.g. the send buffer of an NCCL all-gather) sets it

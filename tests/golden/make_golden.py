@@ -58,8 +58,41 @@ def main():
     np.savez_compressed(os.path.join(OUT, "expected_case1.npz"), **{k: v for k, v in cases})
 
 
+def make_allscales_full():
+    """bank_allScales_full.npz / expected_allScales_full.npz: the reference's own large-bank invocation
+    (linemodLevelup/test.cpp:174-181: Detector() -> T = {5, 8}, 63 features, readClasses(allScales), match at 80) on
+    the fixture frame with ALL 2989 templates, plus threshold 75 (the drivers' value, linemod_and_levelup_test.py:324;
+    61 912 coarse candidates) and the half-occluded frame at 80.  Expected lists by oracle/_ref (the reference's code)."""
+    fe = importlib.import_module("6dpose_b200.frontend")
+    bk = importlib.import_module("6dpose_b200.bank")
+    from oracle import oracle, ref
+    assert ref.build()
+    b = bk.TemplateBank()
+    b.read_class(CASE + "allScales/06_template.yaml", 2)
+    packed = b.pack(b.class_ids(), 4)
+    T = [5, 8]
+    np.savez_compressed(os.path.join(OUT, "bank_allScales_full.npz"), class_begin=packed["class_begin"],
+                        tmeta=packed["tmeta"].astype(np.int32), feats=packed["feats"].astype(np.uint8), T=np.asarray(T, np.int32))
+    assert packed["feats"].max() < 256 and packed["feats"].min() >= 0
+    out = {}
+    for tag, suffix, thresholds in (("full", "", (80.0, 75.0)), ("half", "_half", (80.0,))):
+        rgb = cv2.imread(CASE + "0000_rgb%s.png" % suffix)
+        dep = cv2.imread(CASE + "0000_dep%s.png" % suffix, cv2.IMREAD_UNCHANGED)
+        q = fe.quantize_pyramid([rgb, dep], 2)
+        for thr in thresholds:
+            want, st = ref.match(q, T, packed, thr), None
+            again, st = oracle.match(q, T, packed, thr, want_stats=True)
+            assert np.array_equal(want, again), "restatement and reference disagree"
+            out["%s_%g" % (tag, thr)] = want
+            out["%s_%g_stats" % (tag, thr)] = np.asarray([int(st["coarse_candidates"]), int(st["coarse_byte_adds"]),
+                                                           int(st["refine_byte_adds"])], np.int64)
+            print("allScales full", tag, thr, len(want), want[:2], {k: int(v) for k, v in st.items()})
+    np.savez_compressed(os.path.join(OUT, "expected_allScales_full.npz"), **out)
+
+
 if __name__ == "__main__":
     main()
+    make_allscales_full()
 
 
 def make_train_golden():

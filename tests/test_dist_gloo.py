@@ -85,6 +85,27 @@ def test_sharded_match_equals_single_process(tmp_path, world):
     assert len({(int(r[1]), int(r[2])) for r in res}) == 1   # every rank ends with the same list
 
 
+def test_interleaved_shards_cover_every_template_once(synth):
+    lib = importlib.import_module("6dpose_b200._lib")
+    bank = synth.synth_bank(23, num_features=32, seed=5, class_ids=("01_template", "02_template"))
+    packed = bank.pack(bank.class_ids(), 4)
+    nat = lib.NativeDetector([4, 8], device=-1)
+    nat.load_bank(packed, 4)
+    for world in (1, 2, 3, 8):
+        seen = []
+        for r in range(world):
+            nat.select(None, r, world, lib.SHARD_INTERLEAVED)
+            b, c = nat.shard_range()
+            assert b == r
+            seen += [b + k * world for k in range(c)]
+        assert sorted(seen) == list(range(46))
+    # more shards than templates of a one-class selection: the surplus shards are empty, not an error
+    nat.select([1], 30, 32, lib.SHARD_INTERLEAVED)
+    assert nat.shard_range()[1] == 0
+    with pytest.raises(RuntimeError):
+        nat.select(None, 0, 2, 7)
+
+
 def test_shards_are_balanced_by_features(synth):
     lib = importlib.import_module("6dpose_b200._lib")
     bank = synth.synth_bank(64, num_features=64, seed=5)

@@ -37,6 +37,28 @@ def test_oracle_reproduces_the_reference_golden_vectors(oracle):
     assert nonempty >= 9
 
 
+def load_allscales_full():
+    """The reference's own large-bank invocation (linemodLevelup/test.cpp:174-181): Detector() = 63 features, T = {5, 8},
+    ALL 2989 templates of test/case1/allScales, threshold 80; plus threshold 75 (61 912 coarse candidates)."""
+    b = np.load(os.path.join(GOLD, "bank_allScales_full.npz"))
+    packed = dict(class_begin=b["class_begin"], tmeta=b["tmeta"].astype(np.int32), feats=b["feats"].astype(np.int32))
+    exp = np.load(os.path.join(GOLD, "expected_allScales_full.npz"))
+    cases = [(k.split("_")[0], float(k.split("_")[1]), exp[k], exp[k + "_stats"]) for k in exp.files if not k.endswith("_stats")]
+    return packed, b["T"].tolist(), cases
+
+
+def test_oracle_reproduces_the_full_allscales_golden_vectors(oracle):
+    frames, _, _ = load_golden()
+    packed, T, cases = load_allscales_full()
+    assert int(packed["class_begin"][-1]) == 2989 and len(cases) == 3
+    for tag, thr, want, stats in cases:
+        got, st = oracle.match(frames[tag], T, packed, thr, want_stats=True)
+        assert np.array_equal(got, want), (tag, thr)
+        assert [int(st["coarse_candidates"]), int(st["coarse_byte_adds"]), int(st["refine_byte_adds"])] == stats.tolist()
+    full75 = [c for c in cases if c[0] == "full" and c[1] == 75.0][0]
+    assert len(full75[2]) == 157 and int(full75[3][0]) == 61912   # BASELINE.md section 2's candidate count
+
+
 def test_golden_top_match_sits_on_the_ground_truth_box():
     # GT box of the object in the fixture frame: [331, 130, 65, 64] (linemodLevelup/test.cpp:86)
     _, _, cases = load_golden()
@@ -92,3 +114,21 @@ def test_cuda_path_reproduces_the_reference_golden_vectors():
         for k in ("x", "y", "template_id", "similarity"):
             assert np.array_equal(got[k], want[k]), (bank, tag, thr, k)
         assert np.array_equal(got["class_index"], want["class_idx"])
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_the_full_allscales_golden_vectors():
+    """All 2989 templates of the reference's allScales bank on its fixture frame, thresholds 80 (test.cpp:174-181) and
+    75: match lists bit-identical to the compiled reference, candidate / algorithmic byte counters equal."""
+    lib = importlib.import_module("6dpose_b200._lib")
+    frames, _, _ = load_golden()
+    packed, T, cases = load_allscales_full()
+    nat = lib.NativeDetector(T)
+    nat.load_bank(packed, 4)
+    for tag, thr, want, stats in cases:
+        got = nat.match_quantized(frames[tag], thr)
+        assert len(got) == len(want), (tag, thr)
+        for k in ("x", "y", "template_id", "similarity"):
+            assert np.array_equal(got[k], want[k]), (tag, thr, k)
+        c = nat.counters()
+        assert [c["coarse_candidates"], c["scan_bytes"], c["refine_bytes"]] == stats.tolist(), (tag, thr)

@@ -143,3 +143,67 @@ def test_fused_exchange_three_handles_one_process():
     dets[0].upload_quantized(q)
     dets[0].run(75.0)
     assert dets[0].fetch_records().tobytes() == want.tobytes()
+
+
+def _exchange_over_handles(devices, layout, seeds=(61, 62, 63)):
+    """One handle per entry of `devices` (one shard each), fused exchange through raw device pointers; every handle must
+    end with all shards' records == the unsharded run on devices[0]."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    synth = importlib.import_module("6dpose_b200.synth")
+    lib = importlib.import_module("6dpose_b200._lib")
+    T = [4, 8]
+    bank = synth.synth_bank(150, num_features=150, seed=51, class_ids=("01_template", "02_template", "03_template"))
+    packed = bank.pack(bank.class_ids(), 4)
+    world = len(devices)
+    single = lib.NativeDetector(T, devices[0])
+    single.load_bank(packed, 4)
+    dets = []
+    for r, dev in enumerate(devices):
+        d = lib.NativeDetector(T, dev)
+        d.load_bank(packed, 4)
+        d.select(None, r, world, layout)
+        d.peer_export(world, 4096)
+        dets.append(d)
+    bases = [d.peer_base() for d in dets]
+    for r, d in enumerate(dets):
+        d.peer_connect_local(r, world, bases)
+    covered = sum(d.shard_range()[1] for d in dets)
+    assert covered == 450
+    for seed in seeds:
+        q, _ = synth.synth_frame(640, 480, seed=seed, bank=bank, plant=5, T=T)
+        single.upload_quantized(q)
+        single.run(75.0)
+        want = single.fetch_records()
+        assert len(want) > 30
+        for d in dets:
+            d.upload_quantized(q)
+        for d in dets:
+            d.enqueue(75.0)
+        for d in dets:
+            d.complete()
+        for d in dets:
+            got = d.fetch_records()
+            assert len(got) == len(want)
+            for f in ("x", "y", "similarity", "work"):
+                assert np.array_equal(got[f], want[f]), f
+            assert single.finish(want).tobytes() == d.finish(got).tobytes()
+    for d in dets:
+        d.peer_disconnect()
+
+
+def test_fused_exchange_interleaved_shards_one_device():
+    lib = importlib.import_module("6dpose_b200._lib")
+    _exchange_over_handles([0, 0, 0, 0], lib.SHARD_INTERLEAVED)
+
+
+def test_fused_exchange_over_distinct_devices():
+    """The peer stores of k_refine over real NVLink: one handle per GPU of the box (2..4 distinct devices), both shard
+    layouts.  Skipped on a one-GPU box (the driver's test box); run with `gpurun --gpus 2` (profiles/ holds the log)."""
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    lib = importlib.import_module("6dpose_b200._lib")
+    _exchange_over_handles(list(range(n)), lib.SHARD_CONTIGUOUS)
+    _exchange_over_handles(list(range(n)), lib.SHARD_INTERLEAVED, seeds=(71, 72))

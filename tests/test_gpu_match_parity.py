@@ -69,6 +69,29 @@ def test_match_bit_exact_synthetic(synth, oracle, T, W, H, nf, n, thr):
     assert c["refine_bytes"] == int(st["refine_byte_adds"])
 
 
+def test_bench_workload_3115_templates_bit_exact(synth, oracle):
+    """The workload the headline numbers are quoted on (bench.py, BASELINE.json configs[1]): 3115 templates (89 views x
+    35 variants), 150 features per modality at level 0, T = [4, 8], 640x480 frames of bench.py's ring (seeds 1000 + i),
+    threshold 75 -- and 90 for the candidate-rate sweep.  Match lists and the candidate / algorithmic-byte counters equal
+    the oracle's."""
+    import os
+    T = [4, 8]
+    bank = synth.synth_bank(3115, num_features=150, levels=2, seed=1234, variants=35)
+    nat, packed = _native(T, bank)
+    threads = os.cpu_count() or 1
+    for seed, thr in ((1000, 75.0), (1001, 75.0), (1175, 75.0), (1002, 90.0)):
+        q, planted = synth.synth_frame(640, 480, levels=2, seed=seed, bank=bank, plant=8, T=T)
+        got = nat.match_quantized(q, thr)
+        want, st = oracle.match(q, T, packed, thr, n_threads=threads, want_stats=True)
+        assert len(want) >= len(planted) > 0
+        _assert_same(got, want)
+        c = nat.counters()
+        assert c["templates"] == 3115
+        assert c["coarse_candidates"] == int(st["coarse_candidates"])
+        assert c["scan_bytes"] == int(st["coarse_byte_adds"])
+        assert c["refine_bytes"] == int(st["refine_byte_adds"])
+
+
 def test_match_mixed_kernels_and_ragged_templates(synth, oracle):
     """Templates whose modalities have different sizes / feature counts (never produced by
     cropTemplates, but legal input): unequal template_positions per modality, empty modality,

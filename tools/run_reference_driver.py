@@ -4,11 +4,16 @@
 The script (mode = 'test', linemod_and_levelup_test.py:86-87) needs, besides `linemodLevelup_pybind`,
 the SIXD toolkit (`pysixd`), `params.dataset_params`, the hinterstoisser dataset and an OpenGL renderer,
 none of which ship with the reference checkout.  This harness pre-seeds sys.modules with light stand-ins
-built from the reference's own fixtures (linemodLevelup/test/case1/: the 640x480 test frame, the 127-feature
-bank through readClasses, the pose/depth_ren.png render) and makes cv2's window calls no-ops, then executes
+built from the reference's own fixtures (linemodLevelup/test/case1/: the 640x480 test frame, the allScales
+bank (2989 templates) through readClasses, the pose/depth_ren.png render) and makes cv2's window calls no-ops, then executes
 the script file as-is.  Needs a CUDA device and the reference checkout (default /root/reference).
 
   python tools/run_reference_driver.py [/path/to/6DPose]
+
+tests/test_reference_driver.py runs it two ways: here (no GPU) with the C-ABI handles replaced by oracle-backed
+stand-ins -- which checks the Python surface the unmodified script drives and records every call it makes -- and on the
+GPU box by replaying that recorded call trace (tests/golden/driver_trace.npz) through the real CUDA backend (the script
+itself lives in the reference checkout, which does not travel to the GPU box and must not be copied).
 """
 import os
 import runpy
@@ -20,22 +25,26 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+REF = sys.argv[1] if len(sys.argv) > 1 and os.path.isdir(sys.argv[1]) else "/root/reference"
 CASE = os.path.join(REF, "linemodLevelup", "test", "case1")
 
 K = np.array([[572.4114, 0.0, 325.2611], [0.0, 573.57043, 242.04899], [0.0, 0.0, 1.0]])  # test.cpp:106
 R_REN = np.array([[0.34768538, 0.93761126, 0.0], [0.70540612, -0.26157897, -0.65877056],
                   [-0.61767070, 0.22904489, -0.75234390]])
 T_REN = np.array([[0.0], [0.0], [1000.0]])
+BANK = os.environ.get("LM_DRIVER_BANK", "allScales")  # which fixture bank stands in for the script's linemod_render_up/
 
 
-def main():
+def main(trace=None):
+    """trace: optional dict; every Detector.match / poseRefine.process call of the script is appended to it."""
     # bank directory laid out as the script expects: <base>/linemod_render_up/%s.yaml + {:02d}_info.yaml
     base = "/tmp/lm_b200_driver"
     os.makedirs(os.path.join(base, "linemod_render_up"), exist_ok=True)
-    src = os.path.join(CASE, "127", "06_template.yaml")
+    src = os.path.join(CASE, BANK, "06_template.yaml")
     dst = os.path.join(base, "linemod_render_up", "06_template.yaml")
-    if not os.path.exists(dst):
+    if os.path.lexists(dst) and os.path.realpath(dst) != os.path.realpath(src):
+        os.remove(dst)
+    if not os.path.lexists(dst):
         os.symlink(src, dst)
 
     dp = {"obj_count": 15, "scene_count": 15, "base_path": base, "test_set_fpath": "test_set",
@@ -79,6 +88,27 @@ def main():
     line_orig = cv2.line
     cv2.line = lambda img, p0, p1, *a, **k: line_orig(img, tuple(int(v) for v in p0), tuple(int(v) for v in p1), *a, **k)
 
+    if trace is not None:
+        mod = __import__("linemodLevelup_pybind")
+        trace.update(rgb=rgb, depth=dep.astype(np.uint16), render=ren.astype(np.uint16), match_calls=[], refine_calls=[])
+        det_match, pr_process = mod.Detector.match, mod.poseRefine.process
+
+        def match(self, sources, threshold, class_ids, masks=None):
+            out = det_match(self, sources, threshold, class_ids, masks=masks)
+            trace["match_calls"].append(dict(sources=[np.array(a) for a in sources], threshold=threshold, class_ids=list(class_ids),
+                                             masks=masks, T=list(self.T_at_level), num_features=self.num_features, matches=out))
+            return out
+
+        def process(self, *args):
+            pr_process(self, *args)
+            trace["refine_calls"].append(dict(args=[np.array(a) for a in args], R=self.getR(), t=self.getT(), residual=self.getResidual()))
+
+        mod.Detector.match, mod.poseRefine.process = match, process
+        try:
+            runpy.run_path(os.path.join(REF, "linemod_and_levelup_test.py"), run_name="__main__")
+        finally:
+            mod.Detector.match, mod.poseRefine.process = det_match, pr_process
+        return trace
     runpy.run_path(os.path.join(REF, "linemod_and_levelup_test.py"), run_name="__main__")
 
 
