@@ -362,18 +362,19 @@ class NativeDetector:
         return out
 
     def counters(self):
-        a = (ctypes.c_int64 * 6)()
+        a = (ctypes.c_int64 * 8)()
         check(self._L.lm_counters(self._h, a))
-        keys = ["templates", "coarse_candidates", "scan_bytes", "refine_bytes", "kept", "refine_bytes_read"]
+        keys = ["templates", "coarse_candidates", "scan_bytes", "refine_bytes", "kept", "refine_bytes_read",
+                "filter_dropped_bytes", "filter_bytes_read"]
         return dict(zip(keys, [int(v) for v in a]))
 
     def set_timing(self, slots):
         check(self._L.lm_set_timing(self._h, int(slots)))
 
     def stage_times_us(self):
-        a = (ctypes.c_float * 5)()
+        a = (ctypes.c_float * 8)()
         check(self._L.lm_stage_times(self._h, a))
-        keys = ["linear_memories", "coarse_scan", "offsets", "refine", "total"]
+        keys = ["linear_memories", "coarse_scan", "offsets", "refine", "total", "refine_prep", "refine_filter", "refine_exact"]
         return dict(zip(keys, [float(v) for v in a]))
 
     def stream(self):

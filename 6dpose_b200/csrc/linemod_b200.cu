@@ -75,6 +75,8 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 #define LM_MAX_ROUNDS 5
 #define LM_BITS_SMEM_LIMIT (200 * 1024)
 #define LM_BAND_SMEM_LIMIT (160 * 1024)
+#define LM_CAND_DEFAULT (4ll << 20)  // candidate-list entries allocated up front (x 12 bytes)
+#define LM_TEV 7  // timing events per frame: start, K1, K2, scan, prep, filter, end
 
 struct LevelHost {
   int T = 0, rows = 0, cols = 0, Wd = 0, Hd = 0, plane = 0;
@@ -113,6 +115,16 @@ struct lm_detector {
   std::vector<uint8_t> safe;         // per template: refinement never skips a feature (LL.cpp:1394)
   uint8_t* d_safe = nullptr;
   uint16_t* d_galign = nullptr;      // [G][S][16] feature counts per (address & 15) group
+  // refinement filter (k_refine_filter) on the first refined level lr = L - 2: column-major H-planes + descriptors
+  bool filter_on = true;             // LINEMOD_B200_FILTER=0 switches it off (profiling / A-B runs)
+  bool filter_ok = false;            // the current frame size / bank allow it
+  uint32_t* d_rp = nullptr; size_t rp_words = 0; int rp_nyb = 0;
+  uint32_t* d_rdesc = nullptr;       // per feature of level lr, grouped per template
+  int2* d_rfeat = nullptr;           // per template: first descriptor, count
+  uint2* d_cand = nullptr; int64_t cand_cap = 0;   // ordered candidate list (k_refine_prep)
+  int64_t cand_need = 0;             // candidates of a frame that overflowed the list
+  uint32_t* d_surv = nullptr;        // survivors of the filter [cand_cap]
+  int* d_queue = nullptr;            // [0] next candidate, [1] survivors
   int prep_rows[LM_MAX_LEVELS] = {0}, prep_cols[LM_MAX_LEVELS] = {0};
   bool prepared = false;
   std::vector<TSlot> h_tslot;
@@ -178,7 +190,7 @@ struct lm_detector {
   bool fe_lut = false;
 
   bool timing = false;
-  std::vector<cudaEvent_t> tev;  // timing slots x 5 events (ring)
+  std::vector<cudaEvent_t> tev;  // timing slots x LM_TEV events (ring)
   int64_t timing_runs = 0;
   cudaEvent_t* ev = nullptr;     // the slot used by the run being enqueued
   int64_t launches = 0;
@@ -233,10 +245,16 @@ extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** o
   CU(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&d->ev_upper, cudaEventDisableTiming));
-  CU(cudaMalloc(&d->d_counters, 4 * sizeof(unsigned long long)));
-  CU(cudaMemset(d->d_counters, 0, 4 * sizeof(unsigned long long)));
-  CU(cudaMallocHost(&d->h_counters, 4 * sizeof(unsigned long long)));
-  memset(d->h_counters, 0, 4 * sizeof(unsigned long long));
+  CU(cudaMalloc(&d->d_counters, 8 * sizeof(unsigned long long)));
+  CU(cudaMemset(d->d_counters, 0, 8 * sizeof(unsigned long long)));
+  CU(cudaMallocHost(&d->h_counters, 8 * sizeof(unsigned long long)));
+  memset(d->h_counters, 0, 8 * sizeof(unsigned long long));
+  CU(cudaMalloc(&d->d_queue, 4 * sizeof(int)));
+  CU(cudaMemset(d->d_queue, 0, 4 * sizeof(int)));
+  {
+    const char* f = getenv("LINEMOD_B200_FILTER");
+    d->filter_on = !(f && f[0] == '0');
+  }
   *out = d;
   return LM_OK;
 }
@@ -267,6 +285,7 @@ extern "C" void lm_destroy(lm_detector* d) {
   cudaFree(d->d_items_bits); cudaFree(d->d_items_bytes); cudaFree(d->d_safe); cudaFree(d->d_galign);
   cudaFree(d->d_mask); cudaFree(d->d_raw); cudaFree(d->d_cnt); cudaFree(d->d_off);
   cudaFree(d->d_res_own); cudaFree(d->d_counters);
+  cudaFree(d->d_rp); cudaFree(d->d_rdesc); cudaFree(d->d_rfeat); cudaFree(d->d_cand); cudaFree(d->d_surv); cudaFree(d->d_queue);
   cudaFreeHost(d->h_counters); cudaFreeHost(d->h_res);
   cudaFree(d->d_post_info); cudaFree(d->d_post_out); cudaFree(d->d_post_counts); cudaFree(d->d_post_live);
   cudaFreeHost(d->h_post_out); cudaFreeHost(d->h_post_counts);
@@ -531,6 +550,53 @@ static int prepare_bank(lm_detector* d) {
   if (!galign.empty()) {
     CU(cudaMalloc(&d->d_galign, galign.size() * sizeof(uint16_t)));
     CU(cudaMemcpyAsync(d->d_galign, galign.data(), galign.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, d->stream));
+  }
+  // refinement filter (k_refine_filter) on the first refined level: column-major H-planes [M*8*T*T][nyb][Wd] and one
+  // descriptor per feature = plane word offset (incl. x / T) : 23 | y / T : 9.  Eligible templates ("safe", so that
+  // the 16x16 patch of every feature is a true 2-D window of the level, and at most 511 features at that level) get
+  // bit 1 of their flag byte; the others go to k_refine unfiltered.
+  d->filter_ok = false;
+  std::vector<uint32_t> rdesc;
+  std::vector<int2> rfeat((size_t)d->G, make_int2(0, 0));
+  if (d->filter_on && d->L >= 2) {
+    const int lr = d->L - 2;
+    const LevelHost& lv = d->lv[lr];
+    const int T = lv.T, T2 = T * T;
+    const int nyb = lv.Hd >= 16 ? ((lv.Hd - 16) >> 4) + 1 : 0;
+    const size_t words = (size_t)d->M * 8 * T2 * nyb * lv.Wd;
+    if (lv.Wd % 4 == 0 && lv.Wd >= 16 && lv.Hd >= 16 && lv.Hd <= 512 && words > 0 && words <= (1u << 23)) {
+      d->filter_ok = true;
+      d->rp_nyb = nyb;
+      if (words != d->rp_words) {
+        cudaFree(d->d_rp);
+        d->d_rp = nullptr;
+        d->rp_words = words;
+        CU(cudaMalloc(&d->d_rp, words * 4));
+      }
+      for (int g = 0; g < d->G; ++g) {
+        int nfl = 0;
+        for (int m = 0; m < d->M; ++m) nfl += d->tmeta[((size_t)g * d->S + lr * d->M + m) * 4 + 3];
+        if (!d->safe[g] || nfl < 1 || nfl > 511) continue;
+        d->safe[g] |= 2;
+        rfeat[(size_t)g] = make_int2((int)rdesc.size(), nfl);
+        for (int m = 0; m < d->M; ++m) {
+          const int32_t* tm = &d->tmeta[((size_t)g * d->S + lr * d->M + m) * 4];
+          for (int k = 0; k < tm[3]; ++k) {
+            const int32_t* f = &d->feats[3 * ((size_t)tm[2] + k)];
+            const uint32_t pb = (uint32_t)((m * 8 + f[2]) * T2 + (f[1] % T) * T + (f[0] % T));
+            rdesc.push_back((pb * (uint32_t)nyb * (uint32_t)lv.Wd + (uint32_t)(f[0] / T)) | ((uint32_t)(f[1] / T) << 23));
+          }
+        }
+      }
+    }
+  }
+  cudaFree(d->d_rdesc); d->d_rdesc = nullptr;
+  cudaFree(d->d_rfeat); d->d_rfeat = nullptr;
+  if (d->filter_ok) {
+    CU(cudaMalloc(&d->d_rdesc, std::max<size_t>(rdesc.size(), 1) * 4));
+    CU(cudaMalloc(&d->d_rfeat, std::max<size_t>(rfeat.size(), 1) * sizeof(int2)));
+    if (!rdesc.empty()) CU(cudaMemcpyAsync(d->d_rdesc, rdesc.data(), rdesc.size() * 4, cudaMemcpyHostToDevice, d->stream));
+    if (!rfeat.empty()) CU(cudaMemcpyAsync(d->d_rfeat, rfeat.data(), rfeat.size() * sizeof(int2), cudaMemcpyHostToDevice, d->stream));
   }
   cudaFree(d->d_safe);
   d->d_safe = nullptr;
@@ -842,7 +908,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
                                                    (size_t)px.rank * px.block_bytes);
   }
   if (d->timing && !refine_only) {
-    d->ev = d->tev.data() + 5 * (size_t)(d->timing_runs % (int64_t)(d->tev.size() / 5));
+    d->ev = d->tev.data() + LM_TEV * (size_t)(d->timing_runs % (int64_t)(d->tev.size() / LM_TEV));
     ++d->timing_runs;
   }
   LinMemParams k1;
@@ -919,6 +985,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       bp.capacity = (int)(px.world > 0 ? d->px_cap : d->res_cap);
       bp.shard = d->shard_index;
       bp.counters = d->d_counters;
+      bp.queue = d->d_queue;
       bp.ticket = reinterpret_cast<int*>(d->d_counters + 3);
       const size_t smem_bytes = (size_t)bp.bp_words * 4;
       const bool smem = smem_bytes <= LM_BITS_SMEM_LIMIT;
@@ -957,7 +1024,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     if (!scan_fused) {
       CU(launch_pdl(k_scan_counts, dim3(1), dim3(1024), 0, st, d->d_cnt, d->d_off, n_work,
                     px.world > 0 ? px_block : d->d_res, (int)(px.world > 0 ? d->px_cap : d->res_cap), d->shard_index,
-                    d->d_counters));
+                    d->d_counters, d->d_queue));
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[3], st));
@@ -972,16 +1039,48 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     d->upper_pending = false;
   }
   if (refine_only) {
-    CU(cudaMemsetAsync(d->d_counters, 0, 2 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(d->d_counters, 0, 8 * sizeof(unsigned long long), st));  // [3] (the coarse scan's ticket) is 0 between launches
+    CU(cudaMemsetAsync(d->d_queue, 0, 4 * sizeof(int), st));
     CU(cudaMemsetAsync(&d->d_res->count, 0, sizeof(int32_t), st));
   }
+  const bool filter = d->filter_ok && d->d_rp != nullptr;
+  const LevelHost& lref = d->lv[d->L >= 2 ? d->L - 2 : 0];
+  {
+    // ordered candidate list (+ the filter's H-planes of the first refined level)
+    PrepParams pp;
+    pp.off = d->d_off; pp.mask = d->d_mask;
+    pp.n_work = n_work; pp.nwords = low.nwords;
+    pp.cand = d->d_cand; pp.cand_cap = (int)d->cand_cap;
+    pp.expand_blocks = std::max(1, std::min((n_work + 7) / 8, d->sm_count * 8));
+    pp.lm = lref.d_lm; pp.rp = filter ? d->d_rp : nullptr;
+    pp.Wd = lref.Wd; pp.Hd = lref.Hd; pp.plane = lref.plane; pp.nyb = d->rp_nyb;
+    pp.n_pb = d->M * 8 * lref.T * lref.T;
+    const int plane_blocks = filter ? (int)(((size_t)pp.n_pb * pp.nyb * (pp.Wd / 4) + 255) / 256) : 0;
+    CU(launch_pdl(k_refine_prep, dim3((unsigned)(pp.expand_blocks + plane_blocks)), dim3(256), 0, st, pp));
+    ++d->launches;
+  }
+  if (d->timing && !refine_only) CU(cudaEventRecord(d->ev[4], st));
+  if (filter) {
+    FilterParams fp;
+    fp.rp = d->d_rp; fp.Wd = lref.Wd; fp.nyb = d->rp_nyb;
+    fp.rdesc = d->d_rdesc; fp.rfeat = d->d_rfeat; fp.flags = d->d_safe;
+    fp.tslot = d->d_tslot; fp.work = d->d_work; fp.S = d->S; fp.M = d->M; fp.L = d->L;
+    fp.low = level_dev(low); fp.ref = level_dev(lref);
+    fp.cand = d->d_cand; fp.off = d->d_off; fp.n_work = n_work; fp.cand_cap = (int)d->cand_cap;
+    fp.threshold = threshold;
+    fp.surv = d->d_surv; fp.queue = d->d_queue; fp.counters = d->d_counters;
+    CU(launch_pdl(k_refine_filter, dim3((unsigned)(d->sm_count * 4)), dim3(256), 0, st, fp));
+    ++d->launches;
+  }
+  if (d->timing && !refine_only) CU(cudaEventRecord(d->ev[5], st));
   {
     // persistent grid: the candidate total is read on the device (no host round trip)
     RefineParams rp;
     for (int l = 0; l < d->L; ++l) rp.lv[l] = level_dev(d->lv[l]);
     rp.tslot = d->d_tslot; rp.fbase = d->d_fbase; rp.fxy = d->d_fxy; rp.work = d->d_work;
-    rp.off = d->d_off; rp.mask = d->d_mask; rp.raw = d->d_raw;
-    rp.n_work = n_work; rp.nwords = low.nwords; rp.L = d->L; rp.S = d->S; rp.M = d->M;
+    rp.off = d->d_off; rp.cand = d->d_cand; rp.cand_cap = (int)d->cand_cap; rp.raw = d->d_raw;
+    rp.surv = filter ? d->d_surv : nullptr; rp.queue = d->d_queue;
+    rp.n_work = n_work; rp.L = d->L; rp.S = d->S; rp.M = d->M;
     rp.work_begin = (int)d->work_base;
     rp.work_stride = (int)d->work_stride;
     rp.threshold = threshold;
@@ -998,7 +1097,9 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     // 4 CTAs are resident per SM (64 registers x 256 threads); 16 per SM = four waves of equal shares, which
     // balances the very uneven per-candidate cost (row-wise early exit) better than one persistent wave
     // (measured: 4 -> 251 us, 8 -> 241, 12..32 -> 229)
-    CU(launch_pdl(k_refine, dim3(d->sm_count * 16), dim3(256), 0, st, rp));
+    // behind the filter the work items are its few survivors: four warps share one (k_refine<true>)
+    if (filter) CU(launch_pdl(k_refine<true>, dim3(d->sm_count * 16), dim3(256), 0, st, rp));
+    else CU(launch_pdl(k_refine<false>, dim3(d->sm_count * 16), dim3(256), 0, st, rp));
     ++d->launches;
   }
   if (px.world > 0) {
@@ -1007,7 +1108,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
                   d->d_counters + 2, d->px_timeout_ns));
     ++d->launches;
   }
-  if (d->timing) CU(cudaEventRecord(d->ev[4], st));
+  if (d->timing && !refine_only) CU(cudaEventRecord(d->ev[6], st));
   return LM_OK;
 }
 
@@ -1019,7 +1120,7 @@ static int enqueue_readback(lm_detector* d) {
   const int64_t first = std::min<int64_t>(d->res_cap, LM_FIRST_FETCH);
   CU(cudaMemcpyAsync(d->h_res, d->d_res, sizeof(lm_result_header) + sizeof(lm_record) * (size_t)first,
                      cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(d->h_counters, d->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(d->h_counters, d->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   d->h_valid = first;
   return LM_OK;
 }
@@ -1040,6 +1141,19 @@ static int ensure_run_buffers(lm_detector* d) {
     d->d_raw = nullptr;
     d->raw_elems = need_r;
     CU(cudaMalloc(&d->d_raw, sizeof(uint16_t) * need_r));
+  }
+  // ordered candidate list + survivor list: worst case one entry per (template, cell); capped (a frame that overflows
+  // the cap is redone from k_refine_prep with a larger list, like the result block)
+  {
+    const int64_t worst = std::max<int64_t>(n_work, 1) * low.plane;
+    const int64_t want = std::min<int64_t>(worst, std::max<int64_t>(LM_CAND_DEFAULT, d->cand_need));
+    if (want > d->cand_cap) {
+      cudaFree(d->d_cand); cudaFree(d->d_surv);
+      d->d_cand = nullptr; d->d_surv = nullptr;
+      d->cand_cap = want;
+      CU(cudaMalloc(&d->d_cand, sizeof(uint2) * (size_t)want));
+      CU(cudaMalloc(&d->d_surv, sizeof(uint32_t) * (size_t)want));
+    }
   }
   if (d->px_rank >= 0 && d->res_external) return fail(LM_E_STATE, "lm_set_result_buffer and a connected peer exchange exclude each other");
   if (d->px_rank >= 0 && d->res_cap_own < d->px_cap * d->px_world) {
@@ -1069,20 +1183,31 @@ static int ensure_run_buffers(lm_detector* d) {
 // outputs of the frame are still in place).  The header travels through a stack copy (the pinned staging block is
 // reallocated by ensure_run_buffers) with the new capacity patched in.
 static int grow_and_rerun(lm_detector* d) {
-  if (d->res_external)
-    return fail(LM_E_CAPACITY, "%d records kept, caller's result buffer holds %lld", d->h_res->count, (long long)d->res_cap);
-  if (d->px_rank >= 0) return fail(LM_E_CAPACITY, "%d records kept, the result block holds %lld", d->h_res->count, (long long)d->res_cap);
   lm_result_header hdr = *d->h_res;
+  const bool more_records = (int64_t)hdr.count > d->res_cap;
+  const bool more_cands = (int64_t)hdr.coarse_candidates > d->cand_cap;
+  if (more_records && d->res_external)
+    return fail(LM_E_CAPACITY, "%d records kept, caller's result buffer holds %lld", hdr.count, (long long)d->res_cap);
+  if (d->px_rank >= 0)
+    return fail(LM_E_CAPACITY, "%d records kept of %d candidates: beyond the result block (%lld) or the candidate list (%lld) of a "
+                "connected peer exchange", hdr.count, hdr.coarse_candidates, (long long)d->res_cap, (long long)d->cand_cap);
   CU(cudaStreamSynchronize(d->stream));
-  cudaFree(d->d_res_own);
-  d->d_res_own = nullptr;
-  d->res_cap_own = (int64_t)hdr.count * 2;
-  CU(cudaMalloc(&d->d_res_own, sizeof(lm_result_header) + sizeof(lm_record) * (size_t)d->res_cap_own));
-  hdr.capacity = (int32_t)d->res_cap_own;
-  hdr.count = 0;
-  CU(cudaMemcpy(d->d_res_own, &hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+  if (more_cands) d->cand_need = (int64_t)hdr.coarse_candidates;  // ensure_run_buffers reallocates the lists
+  if (more_records || (more_cands && !d->res_external)) {
+    // with a truncated candidate list the kept count is a lower bound: leave room, a second pass grows again if needed
+    const int64_t want = std::max<int64_t>((int64_t)hdr.count * 2, d->res_cap_own);
+    if (want > d->res_cap_own) {
+      cudaFree(d->d_res_own);
+      d->d_res_own = nullptr;
+      d->res_cap_own = want;
+      CU(cudaMalloc(&d->d_res_own, sizeof(lm_result_header) + sizeof(lm_record) * (size_t)d->res_cap_own));
+    }
+  }
   int rc = ensure_run_buffers(d);
   if (rc) return rc;
+  hdr.capacity = (int32_t)d->res_cap;
+  hdr.count = 0;
+  CU(cudaMemcpy(d->d_res, &hdr, sizeof(hdr), cudaMemcpyHostToDevice));
   rc = enqueue_stages(d, d->last_threshold, true);
   if (rc) return rc;
   rc = enqueue_readback(d);
@@ -1137,7 +1262,7 @@ extern "C" int lm_complete(lm_detector* d) {
       return fail(LM_E_CAPACITY, "peer exchange: a shard kept more than %lld records (capacity given to lm_peer_export)",
                   (long long)d->px_cap);
   }
-  if ((int64_t)d->h_res->count > d->res_cap) {
+  for (int pass = 0; pass < 3 && ((int64_t)d->h_res->count > d->res_cap || (int64_t)d->h_res->coarse_candidates > d->cand_cap); ++pass) {
     rc = grow_and_rerun(d);
     if (rc) return rc;
   }
@@ -1548,7 +1673,7 @@ extern "C" int lm_complete_post(lm_detector* d, lm_match* out, int64_t cap, int6
   // the common top-k is small: fetch a first window with the counts, the rest only if there is more
   const int first = 16;
   CU(cudaMemcpyAsync(d->h_post_out, d->d_post_out, sizeof(lm_match) * first, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(d->h_counters, d->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(d->h_counters, d->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
   d->post_pending = false;
@@ -1557,7 +1682,7 @@ extern "C" int lm_complete_post(lm_detector* d, lm_match* out, int64_t cap, int6
   if (d->px_rank >= 0 && d->h_counters[2] == 2) return fail(LM_E_CAPACITY, "peer exchange: a shard kept more than %lld records", (long long)d->px_cap);
   const int64_t n = d->h_post_counts[0];
   if (n_records) *n_records = d->h_post_counts[1];
-  if ((int64_t)d->h_post_counts[1] > d->res_cap) {
+  if ((int64_t)d->h_post_counts[1] > d->res_cap || (int64_t)d->h_post_counts[3] > d->cand_cap) {
     // the NMS did not see every record: grow the block like lm_complete does, redo the refinement, run the NMS again
     if (d->post_retry || d->res_external || d->px_rank >= 0)
       return fail(LM_E_CAPACITY, "%d records kept, the result block holds %lld: the NMS did not see all of them", d->h_post_counts[1],
@@ -1648,15 +1773,17 @@ extern "C" int lm_debug_linear_memories(lm_detector* d, int level, int modality,
   return LM_OK;
 }
 
-extern "C" int lm_counters(lm_detector* d, int64_t* out5) {  // 6 entries
-  if (!d || !out5) return fail(LM_E_INVALID, "null argument");
+extern "C" int lm_counters(lm_detector* d, int64_t* out8) {
+  if (!d || !out8) return fail(LM_E_INVALID, "null argument");
   if (!d->have_run) return fail(LM_E_STATE, "lm_run has not been called");
-  out5[0] = d->shard_count;
-  out5[1] = d->h_res->coarse_candidates;
-  out5[2] = d->alg_scan_bytes;
-  out5[3] = (int64_t)d->h_counters[0] * 256;
-  out5[4] = d->h_res->count;
-  out5[5] = (int64_t)d->h_counters[1] * 16;
+  out8[0] = d->shard_count;
+  out8[1] = d->h_res->coarse_candidates;
+  out8[2] = d->alg_scan_bytes;
+  out8[3] = (int64_t)(d->h_counters[0] + d->h_counters[4]) * 256;  // the reference's refinement work, whoever disposed of it
+  out8[4] = d->h_res->count;
+  out8[5] = (int64_t)d->h_counters[1] * 16;
+  out8[6] = (int64_t)d->h_counters[4] * 256;  // ... of which: candidates the filter dropped
+  out8[7] = (int64_t)d->h_counters[5] * 4;    // bytes of H-planes the filter read
   return LM_OK;
 }
 
@@ -1669,7 +1796,7 @@ extern "C" int lm_set_timing(lm_detector* d, int slots) {
   d->tev.clear();
   d->timing_runs = 0;
   d->timing = slots > 0;
-  for (int i = 0; i < slots * 5; ++i) {
+  for (int i = 0; i < slots * LM_TEV; ++i) {
     cudaEvent_t e;
     CU(cudaEventCreate(&e));
     d->tev.push_back(e);
@@ -1677,24 +1804,25 @@ extern "C" int lm_set_timing(lm_detector* d, int slots) {
   return LM_OK;
 }
 
-extern "C" int lm_stage_times(lm_detector* d, float* out5) {
-  if (!d || !out5) return fail(LM_E_INVALID, "null argument");
+extern "C" int lm_stage_times(lm_detector* d, float* out8) {
+  if (!d || !out8) return fail(LM_E_INVALID, "null argument");
   if (!d->timing || d->timing_runs == 0) return fail(LM_E_STATE, "timing not enabled / no run recorded");
   CU(cudaSetDevice(d->device));
   CU(cudaStreamSynchronize(d->stream));
-  const int64_t slots = (int64_t)d->tev.size() / 5;
+  const int64_t slots = (int64_t)d->tev.size() / LM_TEV;
   const int64_t n = std::min<int64_t>(slots, d->timing_runs);
-  double acc[5] = {0, 0, 0, 0, 0};
+  // events: 0 start | 1 linear memories | 2 coarse scan | 3 offsets (+ upper-level linear memories) | 4 candidate list +
+  // filter planes | 5 filter | 6 exact refinement (+ collector)
+  static const int from[8] = {0, 1, 2, 3, 0, 3, 4, 5}, to[8] = {1, 2, 3, 6, 6, 4, 5, 6};
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int64_t k = 0; k < n; ++k) {
-    cudaEvent_t* ev = d->tev.data() + 5 * k;
-    float ms;
-    for (int i = 0; i < 4; ++i) {
-      CU(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    cudaEvent_t* ev = d->tev.data() + LM_TEV * k;
+    for (int i = 0; i < 8; ++i) {
+      float ms;
+      CU(cudaEventElapsedTime(&ms, ev[from[i]], ev[to[i]]));
       acc[i] += ms * 1000.0;
     }
-    CU(cudaEventElapsedTime(&ms, ev[0], ev[4]));
-    acc[4] += ms * 1000.0;
   }
-  for (int i = 0; i < 5; ++i) out5[i] = (float)(acc[i] / (double)n);
+  for (int i = 0; i < 8; ++i) out8[i] = (float)(acc[i] / (double)n);
   return LM_OK;
 }

@@ -333,6 +333,7 @@ struct BitScanParams {
   lm_result_header* hdr;
   int capacity, shard;
   unsigned long long* counters;
+  int* queue;      // work / survivor counters of the refinement filter, reset with the header
   int* ticket;     // zero between launches
 };
 
@@ -371,7 +372,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // counts re-zeroed for the next frame's atomics.  Whole CTA.
 __device__ __forceinline__ void scan_counts_block(int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
                                                   lm_result_header* __restrict__ hdr, int capacity, int shard,
-                                                  unsigned long long* __restrict__ counters, int* s_warp) {
+                                                  unsigned long long* __restrict__ counters, int* __restrict__ queue, int* s_warp) {
   const int per = (n + blockDim.x - 1) / blockDim.x;
   const int b = min((int)threadIdx.x * per, n), e = min(b + per, n);
   int sum = 0;
@@ -391,15 +392,19 @@ __device__ __forceinline__ void scan_counts_block(int32_t* __restrict__ cnt, int
     hdr->shard = shard;
     counters[0] = 0ull;  // k_refine accumulates into them
     counters[1] = 0ull;
+    counters[4] = 0ull;  // k_refine_filter: features x candidates it dropped, plane words it read
+    counters[5] = 0ull;
+    queue[0] = 0;        // k_refine_filter: next candidate, survivors appended
+    queue[1] = 0;
   }
 }
 
 __global__ void __launch_bounds__(1024) k_scan_counts(int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
                                                      lm_result_header* __restrict__ hdr, int capacity, int shard,
-                                                     unsigned long long* __restrict__ counters) {
+                                                     unsigned long long* __restrict__ counters, int* __restrict__ queue) {
   lm_pdl_wait();
   __shared__ int s_warp[33];
-  scan_counts_block(cnt, off, n, hdr, capacity, shard, counters, s_warp);
+  scan_counts_block(cnt, off, n, hdr, capacity, shard, counters, queue, s_warp);
 }
 
 // K2 work decomposition.  A template only has ceil(P / 32) position words that can hold a score (P = its
@@ -677,7 +682,7 @@ __global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanPar
     __syncthreads();
     if (s_last) {
       __threadfence();
-      scan_counts_block(p.cnt, p.off, p.n_work, p.hdr, p.capacity, p.shard, p.counters, s_warp);
+      scan_counts_block(p.cnt, p.off, p.n_work, p.hdr, p.capacity, p.shard, p.counters, p.queue, s_warp);
       if (threadIdx.x == 0) *p.ticket = 0;
     }
   }
@@ -799,8 +804,262 @@ __global__ void __launch_bounds__(1024) k_coarse_bytes(ByteScanParams p) {
 }
 
 // --------------------------------------------------------------------------------------------
-// exclusive scan of the per-template candidate counts -> global candidate offsets (ordered)
+// k_refine_prep: (a) the ordered candidate list, (b) the refinement bit-planes of the first refined level
+//
+// (a) The coarse scan leaves a pass mask, raw scores and (after the scan) an offset per template.  The refinement used to
+//     decode "candidate c" from them with a binary search + a select-bit walk per candidate; here one warp per template
+//     writes cand[off[w] + k] = (w, j) for the k-th set bit j once, in the reference's pre-sort order
+//     (template order, then ascending cell; LL.cpp:1797-1852), so c stays the record's `seq`.
+// (b) H-planes for the refinement filter: bit = (response == 4) = spread bit of the label (the SIMILARITY_LUT rule, see
+//     lm_response).  COLUMN-major and overlapping: word (x, yb) of block (modality, label, grid) holds rows
+//     16*yb .. 16*yb + 31 of column x, so the 16 rows of ANY 16x16 patch column are bits s .. s+15 of ONE word, and the 16
+//     columns of a patch are 16 consecutive words (64 contiguous bytes) -- against 16 rows x 16 bytes in 16 different
+//     128-byte lines of the byte linear memories.
 // --------------------------------------------------------------------------------------------
+struct PrepParams {
+  const int32_t* off;    // [n_work + 1]
+  const uint32_t* mask;  // [n_work][nwords]
+  int n_work, nwords;
+  uint2* cand;
+  int cand_cap;
+  int expand_blocks;     // blocks [0, expand_blocks) expand, the others build planes
+  const uint8_t* lm;     // byte linear memories of the filtered level, [M*8*T*T][plane]
+  uint32_t* rp;          // [M*8*T*T][nyb][Wd], null: no planes
+  int Wd, Hd, plane, nyb, n_pb;
+};
+
+__global__ void __launch_bounds__(256) k_refine_prep(PrepParams p) {
+  lm_pdl_wait();
+  const int lane = threadIdx.x & 31;
+  if ((int)blockIdx.x < p.expand_blocks) {
+    const int nw = (p.expand_blocks * 256) >> 5;
+    for (int w = (blockIdx.x * 256 + threadIdx.x) >> 5; w < p.n_work; w += nw) {
+      const int base = p.off[w];
+      if (p.off[w + 1] == base) continue;
+      const uint32_t* __restrict__ mk = p.mask + (size_t)w * p.nwords;
+      int run = 0;
+      for (int b0 = 0; b0 < p.nwords; b0 += 32) {
+        uint32_t word = (b0 + lane < p.nwords) ? mk[b0 + lane] : 0u;
+        const int pc = __popc(word);
+        int inc = pc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += t;
+        }
+        int idx = base + run + inc - pc;
+        while (word) {
+          const int j = (b0 + lane) * 32 + __ffs(word) - 1;
+          word &= word - 1;
+          if (idx < p.cand_cap) p.cand[idx] = make_uint2((uint32_t)w, (uint32_t)j);  // stores only: nothing to wait for
+          ++idx;
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    return;
+  }
+  if (!p.rp) return;
+  // planes: one thread = 4 neighbouring columns of one word row (32-bit loads of 4 response bytes, one 128-bit store)
+  const int wq = p.Wd >> 2;
+  const int n = p.n_pb * p.nyb * wq;
+  const int t = ((int)blockIdx.x - p.expand_blocks) * 256 + (int)threadIdx.x;
+  if (t >= n) return;
+  const int x4 = t % wq, yb = (t / wq) % p.nyb, pb = t / (wq * p.nyb);
+  const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(p.lm + (size_t)pb * p.plane) + x4;
+  uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+  const int r0 = 16 * yb;
+#pragma unroll 8
+  for (int b = 0; b < 32; ++b) {
+    const int r = r0 + b;
+    const uint32_t v = (r < p.Hd) ? __ldg(src + (size_t)r * wq) : 0u;
+    o0 |= ((v >> 2) & 1u) << b;
+    o1 |= ((v >> 10) & 1u) << b;
+    o2 |= ((v >> 18) & 1u) << b;
+    o3 |= ((v >> 26) & 1u) << b;
+  }
+  *reinterpret_cast<uint4*>(p.rp + ((size_t)pb * p.nyb + yb) * p.Wd + 4 * x4) = make_uint4(o0, o1, o2, o3);
+}
+
+// --------------------------------------------------------------------------------------------
+// k_refine_filter: exact upper-bound test in front of the refinement, bit-sliced.
+//
+// similarityLocal adds, per feature, 4 where the feature's label bit is set in the spread mask (H), else at most 1
+// (LL.cpp:1121 table; lm_response).  So for every cell of the 16x16 patch  raw <= 4*CH + (nf - CH) = 3*CH + nf  with CH =
+// number of features whose H bit is set at that cell.  A candidate survives remove_if (LL.cpp:1935-1937) only if its best
+// cell reaches raw_keep, i.e. only if SOME cell has CH >= need = ceil((raw_keep - nf) / 3).  Candidates without such a cell
+// are dropped here without ever touching the byte linear memories; the others (a few percent) go on to k_refine, which
+// computes them exactly as before -- the filter never changes a result, it only removes work.
+//
+// Eight lanes own one candidate (four candidates per warp): lane k holds patch columns k and k + 8 as the two halves of
+// a 32-bit word (16 rows each) and counts CH for its 32 cells in a 9-bit vertical counter (carry-save adders, 8 features
+// per step).  Per feature and lane: two 32-bit loads from the column-major H-planes (k_refine_prep), two shifts, one
+// byte-permute.  Every 32 features the cells that cannot reach `need` any more (CH + remaining < need) are found with a
+// bit-sliced compare; a lane without live cells stops loading, a candidate without live cells is dropped at once.  The
+// four groups of a warp run independently: each fetches its next candidate from a global counter when it is done.
+// --------------------------------------------------------------------------------------------
+struct FilterParams {
+  const uint32_t* rp;      // H-planes of the filtered level
+  int Wd, nyb;
+  const uint32_t* rdesc;   // per feature (own order, grouped per template): plane word offset incl. x / T : 23 | y / T : 9
+  const int2* rfeat;       // per template: first descriptor, number of features of the level (all modalities)
+  const uint8_t* flags;    // per template: bit 0 = "safe" (k_refine's fast path), bit 1 = the filter may take it
+  const TSlot* tslot;
+  const int32_t* work;
+  int S, M, L;
+  LevelDev low, ref;       // lowest level (cell -> pixel), filtered level (clamp, patch origin)
+  const uint2* cand;
+  const int32_t* off;
+  int n_work, cand_cap;
+  float threshold;
+  uint32_t* surv;          // survivors (candidate indices), unordered
+  int* queue;              // [0] next candidate, [1] survivors
+  unsigned long long* counters;  // [4] features x candidates dropped here, [5] plane words read
+};
+
+// add eight 1-bit planes into an NB-bit vertical counter
+template <int NB>
+__device__ __forceinline__ void vc_add8n(uint32_t (&c)[NB], const uint32_t (&x)[8]) {
+  uint32_t t1a, t1b, t1c, t1d, t2a, t2b, t3;
+  CSA(c[0], t1a, c[0], x[0], x[1]);
+  CSA(c[0], t1b, c[0], x[2], x[3]);
+  CSA(c[1], t2a, c[1], t1a, t1b);
+  CSA(c[0], t1c, c[0], x[4], x[5]);
+  CSA(c[0], t1d, c[0], x[6], x[7]);
+  CSA(c[1], t2b, c[1], t1c, t1d);
+  CSA(c[2], t3, c[2], t2a, t2b);
+#pragma unroll
+  for (int b = 3; b < NB; ++b) {
+    const uint32_t k = c[b] & t3;
+    c[b] ^= t3;
+    t3 = k;
+  }
+}
+
+#define LM_FILTER_BITS 9   // CH <= 511 features of the filtered level
+
+__global__ void __launch_bounds__(256, 4) k_refine_filter(FilterParams p) {
+  lm_pdl_wait();
+  const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+  const unsigned gmask = 0xFFu << (grp * 8);
+  const int total = min(p.off[p.n_work], p.cand_cap);
+  const int lr = p.L - 2;
+  int c = -1, nf = 0, first = 0, need = 0, i = 0, base0 = 0, cy = 0;
+  bool exhausted = false, lane_alive = false;
+  uint32_t ch[LM_FILTER_BITS];
+#pragma unroll
+  for (int b = 0; b < LM_FILTER_BITS; ++b) ch[b] = 0u;
+  unsigned words_read = 0, dropped_feats = 0;
+
+  for (;;) {
+    // ---- groups without a candidate fetch the next one (one atomic per warp and round)
+    const bool want = c < 0 && !exhausted;
+    const unsigned fetch = __ballot_sync(0xffffffffu, want && gl == 0);
+    if (fetch) {
+      const int leader = __ffs(fetch) - 1;
+      int basec = 0;
+      if (lane == leader) basec = atomicAdd(p.queue, __popc(fetch));
+      basec = __shfl_sync(0xffffffffu, basec, leader);
+      if (want) {
+        const int cc = basec + __popc(fetch & ((1u << (grp * 8)) - 1u));
+        if (cc >= total) {
+          exhausted = true;
+        } else {
+          const uint2 e = __ldcg(p.cand + cc);
+          const int w = (int)e.x, j = (int)e.y;
+          const int g = p.work[w];
+          bool pass = true;  // hand the candidate to k_refine unfiltered
+          if (p.flags[g] & 2) {
+            const int2 rf = p.rfeat[g];
+            nf = rf.y;
+            first = rf.x;
+            const int raw_keep = lm_min_kept_raw(p.threshold, nf);
+            need = raw_keep - nf;
+            need = need > 0 ? (need + 2) / 3 : 0;
+            if (need > nf) {  // nothing can be kept (LL.cpp:1935-1937 would drop whatever the patch holds)
+              if (gl == 0) dropped_feats += (unsigned)nf;
+              pass = false;
+            } else if (need > 0) {
+              // patch origin of the candidate at the filtered level (LL.cpp:1871-1880, 1380-1381)
+              const TSlot t0 = p.tslot[(size_t)g * p.S + lr * p.M];
+              const int T = p.ref.T, border = 8 * T;
+              int x = (j % p.low.Wd) * p.low.T + p.low.off;
+              int y = (j / p.low.Wd) * p.low.T + p.low.off;
+              x = x * 2 + 1;
+              y = y * 2 + 1;
+              x = max(x, border); y = max(y, border);
+              x = min(x, p.ref.cols - (t0.w & 0xFFFF) - border);
+              y = min(y, p.ref.rows - (int)((unsigned)t0.w >> 16) - border);
+              base0 = x / T - 8 + gl;
+              cy = y / T - 8;
+              i = 0;
+              lane_alive = true;
+#pragma unroll
+              for (int b = 0; b < LM_FILTER_BITS; ++b) ch[b] = 0u;
+              c = cc;
+              pass = false;
+            }
+          }
+          if (pass && gl == 0) p.surv[atomicAdd(p.queue + 1, 1)] = (uint32_t)cc;
+        }
+      }
+    }
+    if (__all_sync(0xffffffffu, c < 0 && exhausted)) break;
+
+    // ---- one step: 8 features of every group that holds a candidate
+    const bool act = c >= 0;
+    uint32_t xh[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      uint32_t h = 0u;
+      if (act && lane_alive && i + u < nf) {
+        const uint32_t d = __ldg(p.rdesc + first + i + u);
+        const int py0 = cy + (int)(d >> 23);
+        const uint32_t* __restrict__ ptr = p.rp + (d & 0x7FFFFFu) + (py0 >> 4) * p.Wd + base0;
+        const uint32_t sft = (uint32_t)py0 & 15u;
+        h = __byte_perm(__ldg(ptr) >> sft, __ldg(ptr + 8) >> sft, 0x5410);
+        words_read += 2;
+      }
+      xh[u] = h;
+    }
+    vc_add8n<LM_FILTER_BITS>(ch, xh);
+    if (act) {
+      i += 8;
+      const bool end = i >= nf;
+      if (end || (i & 31) == 0) {
+        // cells that can still reach `need`: CH >= need - (features not yet added)
+        const int thr_now = need - (nf - min(i, nf));
+        uint32_t alive_cells = 0xffffffffu;
+        if (thr_now > 0) {
+          uint32_t gt = 0u, eq = 0xffffffffu;
+#pragma unroll
+          for (int b = LM_FILTER_BITS - 1; b >= 0; --b) {
+            const uint32_t tb = 0u - (((uint32_t)thr_now >> b) & 1u);
+            gt |= eq & ch[b] & ~tb;
+            eq &= ~(ch[b] ^ tb);
+          }
+          alive_cells = gt | eq;
+        }
+        lane_alive = alive_cells != 0u;
+        const unsigned g_alive = __ballot_sync(gmask, lane_alive);
+        if (g_alive == 0u) {
+          if (gl == 0) dropped_feats += (unsigned)nf;  // the reference's work for it (algorithmic bytes / 256)
+          c = -1;
+        } else if (end) {
+          if (gl == 0) p.surv[atomicAdd(p.queue + 1, 1)] = (uint32_t)c;
+          c = -1;
+        }
+      }
+    }
+  }
+  words_read = __reduce_add_sync(0xffffffffu, words_read);
+  dropped_feats = __reduce_add_sync(0xffffffffu, dropped_feats);
+  if (lane == 0 && (words_read | dropped_feats)) {
+    atomicAdd(p.counters + 4, (unsigned long long)dropped_feats);
+    atomicAdd(p.counters + 5, (unsigned long long)words_read);
+  }
+}
+
 
 // --------------------------------------------------------------------------------------------
 // K3: local refinement, one warp per coarse candidate, all upper pyramid levels
@@ -856,16 +1115,19 @@ struct RefineParams {
   const uint32_t* fxy;
   const int32_t* work;
   const int32_t* off;    // [n_work + 1]
-  const uint32_t* mask;  // [n_work][nwords]
-  const uint16_t* raw;   // [n_work][plane_low]
-  int n_work, nwords, L, S, M;
+  const uint2* cand;     // ordered candidate list (k_refine_prep)
+  int cand_cap;
+  const uint16_t* raw;   // [n_work][plane_low] coarse raw scores (read when there is no level to refine)
+  const uint32_t* surv;  // survivors of k_refine_filter, or null: every candidate
+  const int* queue;      // [1] number of survivors
+  int n_work, L, S, M;
   int work_begin, work_stride;  // entry w of this shard is element work_begin + w * work_stride of the selected sequence
   float threshold;
   lm_result_header* hdr;  // result block: header, then `capacity` records
   int32_t capacity;
   unsigned long long* counters;  // [0] features x candidates of the reference's refinement (x256 = algorithmic
                                  // bytes), [1] feature x patch rows actually read (row-wise early exit; x16 bytes)
-  const uint8_t* safe;           // per template: no feature can leave the image once a clamped patch
+  const uint8_t* safe;           // per template, bit 0: no feature can leave the image once a clamped patch
                                  // offset is applied (LL.cpp:1394 never skips) -> 128-bit row loads
   const uint16_t* galign;        // [G][S][16]: features per (fbase & 15) group (refined levels are stored
                                  // grouped by it)
@@ -914,11 +1176,22 @@ __device__ __forceinline__ void refine_rows(const uint4* __restrict__ lm128, con
 #ifndef LM_REFINE_MIN_CTAS
 #define LM_REFINE_MIN_CTAS 4
 #endif
+// kSplit = false: one warp per candidate, exact row-wise early exit (every coarse candidate comes here: no filter).
+// kSplit = true : the work items are the filter's survivors -- few (a few percent of the candidates) and nearly all of
+//   them kept, so the early exit has nothing to skip and ONE warp per candidate would leave the kernel waiting on a
+//   single warp's chain of 300 dependent row loads.  Four warps share a candidate instead: warp q adds the features of the
+//   alignment groups q, q + 4, q + 8, q + 12 (the features of a refined level are stored grouped by address & 15), the
+//   partial 16x16 sums meet in shared memory, every warp of the quad finishes the candidate redundantly (same best cell,
+//   same position for the next level) and warp 0 of the quad appends the record.
+template <bool kSplit>
 __global__ void __launch_bounds__(256, LM_REFINE_MIN_CTAS) k_refine(RefineParams p) {
   lm_pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int total = p.off[p.n_work];
+  constexpr int Q = kSplit ? 4 : 1;
+  __shared__ uint4 s_part[kSplit ? 8 : 1][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = kSplit ? (warp & 3) : 0;
+  const int per_cta = kSplit ? 2 : 8;  // candidates in flight per CTA
+  const int total = min(p.off[p.n_work], p.cand_cap);
   const LevelDev low = p.lv[p.L - 1];
   const int row = lane >> 1, half = lane & 1;
   unsigned feats_done = 0, rows_read = 0;  // per warp: a few candidates x (features x 16 rows)
@@ -926,183 +1199,182 @@ __global__ void __launch_bounds__(256, LM_REFINE_MIN_CTAS) k_refine(RefineParams
   if (p.bp_clear)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.bp_words; i += gridDim.x * blockDim.x) p.bp_clear[i] = 0u;
 
-  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < total; c += nwarps) {
-    // template of candidate c: last w with off[w] <= c
-    int lo = 0, hi = p.n_work;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (p.off[mid] <= c) lo = mid; else hi = mid;
-    }
-    const int w = lo;
-    const int g = p.work[w];
-    // the (c - off[w])-th set bit of the template's pass mask, in position order
-    int j;
-    {
-      int k = c - p.off[w];
-      const uint32_t* __restrict__ mk = p.mask + (size_t)w * p.nwords;
-      j = 0;
-      for (int base = 0; base < p.nwords; base += 32) {
-        const uint32_t word = (base + lane < p.nwords) ? mk[base + lane] : 0u;
-        const int pc = __popc(word);
-        int inc = pc;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, inc, d);
-          if (lane >= d) inc += t;
-        }
-        const int tot = __shfl_sync(0xffffffffu, inc, 31);
-        if (k < tot) {
-          const uint32_t hit = __ballot_sync(0xffffffffu, k < inc);
-          const int src = __ffs(hit) - 1;  // first lane whose inclusive prefix exceeds k
-          const int before = __shfl_sync(0xffffffffu, inc - pc, src);
-          const uint32_t wsel = __shfl_sync(0xffffffffu, word, src);
-          j = (base + src) * 32 + (int)__fns(wsel, 0, k - before + 1);
-          break;
-        }
-        k -= tot;
+  // work items: the survivors of k_refine_filter (unordered candidate indices), or every candidate
+  const int n_items = p.surv ? min(__ldcg(p.queue + 1), total) : total;
+  for (int base = blockIdx.x * per_cta; base < n_items; base += gridDim.x * per_cta) {
+    const int it = base + (kSplit ? (warp >> 2) : warp);
+    const bool valid = it < n_items;
+    if (!kSplit && !valid) break;
+    int c = 0, w = 0, g = 0, x = 0, y = 0;
+    float sim = 0.f;
+    if (valid) {
+      c = p.surv ? (int)__ldcg(p.surv + it) : it;
+      const uint2 ce = __ldcg(p.cand + c);  // (work item, cell), written in pre-sort order by k_refine_prep
+      w = (int)ce.x;
+      const int j = (int)ce.y;
+      g = p.work[w];
+      x = (j % low.Wd) * low.T + low.off;
+      y = (j / low.Wd) * low.T + low.off;
+      if (p.L == 1) {  // the coarse similarity is the result only when nothing is refined (one pyramid level)
+        int nfeat = 0;
+        for (int m = 0; m < p.M; ++m) nfeat += p.tslot[(size_t)g * p.S + (p.L - 1) * p.M + m].y;
+        sim = lm_score((int)p.raw[(size_t)w * low.plane + j], nfeat);
       }
     }
-    int nfeat = 0;
-    for (int m = 0; m < p.M; ++m) nfeat += p.tslot[(size_t)g * p.S + (p.L - 1) * p.M + m].y;
-    int x = (j % low.Wd) * low.T + low.off;
-    int y = (j / low.Wd) * low.T + low.off;
-    float sim = lm_score((int)p.raw[(size_t)w * low.plane + j], nfeat);
-    bool kept = true;
+    bool kept = valid;
 
-    for (int l = p.L - 2; l >= 0 && kept; --l) {
+    for (int l = p.L - 2; l >= 0 && (kSplit || kept); --l) {
       const LevelDev lv = p.lv[l];
-      const uint32_t* __restrict__ lm32 = reinterpret_cast<const uint32_t*>(lv.lm);
-      const TSlot t0 = p.tslot[(size_t)g * p.S + l * p.M];
-      const int T = lv.T, border = 8 * T;
-      const int max_x = lv.cols - (t0.w & 0xFFFF) - border;
-      const int max_y = lv.rows - (int)((unsigned)t0.w >> 16) - border;
-      x = x * 2 + 1;
-      y = y * 2 + 1;
-      x = max(x, border); y = max(y, border);  // LL.cpp:1875-1880 (max first, then min)
-      x = min(x, max_x);  y = min(y, max_y);
-      const int cx = x / T - 8, cy = y / T - 8;  // truncating division, LL.cpp:1380-1381
-      const int ox = cx * T, oy = cy * T;
-      const int shift = cy * lv.Wd + cx + row * lv.Wd + half * 8;
-
+      const int T = lv.T;
       uint32_t s01 = 0, s23 = 0, s45 = 0, s67 = 0;
-      int nf2 = 0;
+      int nf_level = 0;
       bool pruned = false;
-      if (p.safe[g] && (lv.Wd & 15) == 0) {
-        // Fast path.  Every row of the 16x16 patch starts at the same offset inside its 16-byte
-        // chunk (Wd is a multiple of 16), so the two lanes of a row fetch the two aligned chunks that
-        // hold the row's 16 bytes with ONE 128-bit load each and trade the words they are missing.
-        // The features of a template are stored grouped by (address & 15), so the word offset of the
-        // row start (which decides who trades what) is constant over a whole group of features.
-        const uint4* __restrict__ lm128 = reinterpret_cast<const uint4*>(lv.lm);
-        const uint32_t shift_row = (uint32_t)(cy * lv.Wd + cx + row * lv.Wd);
-        // Early exit (exact), per patch row: a candidate only produces output if its best cell reaches raw_keep.
-        // Every remaining feature adds at most 4 to any cell, so a ROW whose best cell so far + 4 * remaining
-        // falls short can never hold the best cell of a kept candidate: its lane pair stops loading (its stale
-        // sums stay below raw_keep, so they can neither win nor tie).  When no row is left the candidate is
-        // dropped (LL.cpp:1935-1937) whatever the rest adds.  Tested every LM_REFINE_CHECK features.
-        int nf_level = 0;
-        for (int m = 0; m < p.M; ++m) nf_level += p.tslot[(size_t)g * p.S + l * p.M + m].y;
-        const int raw_keep = lm_min_kept_raw(p.threshold, nf_level);
-        int done = 0, since = 0;
-        bool alive = true;
-        unsigned rows_alive = 16;
-        feats_done += nf_level;  // the reference's work for this candidate (algorithmic bytes / 256)
-        for (int m = 0; m < p.M && !pruned; ++m) {
-          const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
-          nf2 += ts.y;
-          const uint32_t* __restrict__ fb = p.fbase + ts.x;
-          const uint16_t* __restrict__ ga = p.galign + ((size_t)g * p.S + l * p.M + m) * 16;
-          uint32_t a8 = 0, b8 = 0;
-          int pend = 0;
-          for (int grp = 0; grp < 16 && !pruned; ++grp) {
-            int n = ga[grp];
-            const uint32_t o = ((uint32_t)grp + shift_row) & 15u;
-            const uint32_t sh = (o & 3u) << 3;
-            while (n > 0) {
-              const int take = min(n, LM_REFINE_CHECK - pend);
-              switch (o >> 2) {
-                case 0: refine_rows<0>(lm128, fb, take, shift_row, half, sh, alive, a8, b8); break;
-                case 1: refine_rows<1>(lm128, fb, take, shift_row, half, sh, alive, a8, b8); break;
-                case 2: refine_rows<2>(lm128, fb, take, shift_row, half, sh, alive, a8, b8); break;
-                default: refine_rows<3>(lm128, fb, take, shift_row, half, sh, alive, a8, b8); break;
+      if (kept) {
+        const uint32_t* __restrict__ lm32 = reinterpret_cast<const uint32_t*>(lv.lm);
+        const TSlot t0 = p.tslot[(size_t)g * p.S + l * p.M];
+        const int border = 8 * T;
+        const int max_x = lv.cols - (t0.w & 0xFFFF) - border;
+        const int max_y = lv.rows - (int)((unsigned)t0.w >> 16) - border;
+        x = x * 2 + 1;
+        y = y * 2 + 1;
+        x = max(x, border); y = max(y, border);  // LL.cpp:1875-1880 (max first, then min)
+        x = min(x, max_x);  y = min(y, max_y);
+        const int cx = x / T - 8, cy = y / T - 8;  // truncating division, LL.cpp:1380-1381
+        const int ox = cx * T, oy = cy * T;
+        const int shift = cy * lv.Wd + cx + row * lv.Wd + half * 8;
+        for (int m = 0; m < p.M; ++m) nf_level += p.tslot[(size_t)g * p.S + l * p.M + m].y;  // all features, skipped or not (LL.cpp:1888)
+
+        if ((p.safe[g] & 1) && (lv.Wd & 15) == 0) {
+          // Fast path.  Every row of the 16x16 patch starts at the same offset inside its 16-byte
+          // chunk (Wd is a multiple of 16), so the two lanes of a row fetch the two aligned chunks that
+          // hold the row's 16 bytes with ONE 128-bit load each and trade the words they are missing.
+          // The features of a template are stored grouped by (address & 15), so the word offset of the
+          // row start (which decides who trades what) is constant over a whole group of features.
+          const uint4* __restrict__ lm128 = reinterpret_cast<const uint4*>(lv.lm);
+          const uint32_t shift_row = (uint32_t)(cy * lv.Wd + cx + row * lv.Wd);
+          // Early exit (exact, kSplit = false only), per patch row: a candidate only produces output if its best cell
+          // reaches raw_keep.  Every remaining feature adds at most 4 to any cell, so a ROW whose best cell so far +
+          // 4 * remaining falls short can never hold the best cell of a kept candidate: its lane pair stops loading (its
+          // stale sums stay below raw_keep, so they can neither win nor tie).  When no row is left the candidate is
+          // dropped (LL.cpp:1935-1937) whatever the rest adds.  Tested every LM_REFINE_CHECK features.
+          const int raw_keep = lm_min_kept_raw(p.threshold, nf_level);
+          int done = 0, since = 0;
+          bool alive = true;
+          unsigned rows_alive = 16;
+          if (q == 0) feats_done += nf_level;  // the reference's work for this candidate (algorithmic bytes / 256)
+          for (int m = 0; m < p.M && !pruned; ++m) {
+            const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
+            const uint32_t* __restrict__ fb = p.fbase + ts.x;
+            const uint16_t* __restrict__ ga = p.galign + ((size_t)g * p.S + l * p.M + m) * 16;
+            uint32_t a8 = 0, b8 = 0;
+            int pend = 0;
+            for (int grp = 0; grp < 16 && !pruned; ++grp) {
+              int n = ga[grp];
+              if (kSplit && (grp & (Q - 1)) != q) {  // another warp of the quad owns this alignment group
+                fb += n;
+                continue;
               }
-              fb += take;
-              n -= take;
-              pend += take;
-              done += take;
-              since += take;
-              if (pend == LM_REFINE_CHECK) {  // <= 63: 63 * 4 = 252, no carry between packed bytes
+              const uint32_t o = ((uint32_t)grp + shift_row) & 15u;
+              const uint32_t sh = (o & 3u) << 3;
+              while (n > 0) {
+                const int take = min(n, LM_REFINE_CHECK - pend);
+                switch (o >> 2) {
+                  case 0: refine_rows<0>(lm128, fb, take, shift_row, half, sh, alive, a8, b8); break;
+                  case 1: refine_rows<1>(lm128, fb, take, shift_row, half, sh, alive, a8, b8); break;
+                  case 2: refine_rows<2>(lm128, fb, take, shift_row, half, sh, alive, a8, b8); break;
+                  default: refine_rows<3>(lm128, fb, take, shift_row, half, sh, alive, a8, b8); break;
+                }
+                fb += take;
+                n -= take;
+                pend += take;
+                done += take;
+                since += take;
+                if (pend == LM_REFINE_CHECK) {  // <= 63: 63 * 4 = 252, no carry between packed bytes
+                  s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
+                  s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
+                  a8 = b8 = 0;
+                  pend = 0;
+                  if (!kSplit) {
+                    uint32_t mx = max(max(max(s01 & 0xFFFF, s01 >> 16), max(s23 & 0xFFFF, s23 >> 16)),
+                                      max(max(s45 & 0xFFFF, s45 >> 16), max(s67 & 0xFFFF, s67 >> 16)));
+                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));  // the row's 16 cells
+                    rows_read += (unsigned)since * rows_alive;
+                    since = 0;
+                    alive = alive && ((int)mx + 4 * (nf_level - done) >= raw_keep);
+                    const unsigned live = __ballot_sync(0xffffffffu, alive);
+                    rows_alive = (unsigned)__popc(live) >> 1;
+                    if (live == 0u) { pruned = true; break; }
+                  }
+                }
+              }
+            }
+            s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
+            s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
+          }
+          rows_read += (unsigned)since * rows_alive;
+        } else {
+          for (int m = 0; m < p.M; ++m) {
+            const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
+            uint32_t a8 = 0, b8 = 0;
+            int pend = 0;
+            for (int i = q; i < ts.y; i += Q) {
+              const uint32_t xy = __ldg(p.fxy + ts.x + i);
+              const int fx = (int)(xy & 0x7FFFu) + ox, fy = (int)((xy >> 16) & 0x7FFFu) + oy;
+              if (fx < 0 || fy < 0 || fx >= lv.cols || fy >= lv.rows) continue;  // LL.cpp:1394
+              const uint32_t a = __ldg(p.fbase + ts.x + i) + (uint32_t)shift;
+              const uint32_t w0 = __ldg(lm32 + (a >> 2));
+              const uint32_t w1 = __ldg(lm32 + (a >> 2) + 1);
+              const uint32_t w2 = __ldg(lm32 + (a >> 2) + 2);
+              const uint32_t sh = (a & 3u) << 3;
+              a8 += __funnelshift_r(w0, w1, sh);
+              b8 += __funnelshift_r(w1, w2, sh);
+              ++feats_done;
+              rows_read += 16;
+              if (++pend == 63) {
                 s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
                 s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
                 a8 = b8 = 0;
                 pend = 0;
-                uint32_t mx = max(max(max(s01 & 0xFFFF, s01 >> 16), max(s23 & 0xFFFF, s23 >> 16)),
-                                  max(max(s45 & 0xFFFF, s45 >> 16), max(s67 & 0xFFFF, s67 >> 16)));
-                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));  // the row's 16 cells
-                rows_read += (unsigned)since * rows_alive;
-                since = 0;
-                alive = alive && ((int)mx + 4 * (nf_level - done) >= raw_keep);
-                const unsigned live = __ballot_sync(0xffffffffu, alive);
-                rows_alive = (unsigned)__popc(live) >> 1;
-                if (live == 0u) { pruned = true; break; }
               }
             }
-          }
-          s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
-          s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
-        }
-        rows_read += (unsigned)since * rows_alive;
-        nf2 = nf_level;
-      } else
-      for (int m = 0; m < p.M; ++m) {
-        const TSlot ts = p.tslot[(size_t)g * p.S + l * p.M + m];
-        nf2 += ts.y;
-        uint32_t a8 = 0, b8 = 0;
-        int pend = 0;
-        for (int i = 0; i < ts.y; ++i) {
-          const uint32_t xy = __ldg(p.fxy + ts.x + i);
-          const int fx = (int)(xy & 0x7FFFu) + ox, fy = (int)((xy >> 16) & 0x7FFFu) + oy;
-          if (fx < 0 || fy < 0 || fx >= lv.cols || fy >= lv.rows) continue;  // LL.cpp:1394
-          const uint32_t a = __ldg(p.fbase + ts.x + i) + (uint32_t)shift;
-          const uint32_t w0 = __ldg(lm32 + (a >> 2));
-          const uint32_t w1 = __ldg(lm32 + (a >> 2) + 1);
-          const uint32_t w2 = __ldg(lm32 + (a >> 2) + 2);
-          const uint32_t sh = (a & 3u) << 3;
-          a8 += __funnelshift_r(w0, w1, sh);
-          b8 += __funnelshift_r(w1, w2, sh);
-          ++feats_done;
-          rows_read += 16;
-          if (++pend == 63) {
             s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
             s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
-            a8 = b8 = 0;
-            pend = 0;
           }
         }
-        s01 += __byte_perm(a8, 0, 0x4140); s23 += __byte_perm(a8, 0, 0x4342);
-        s45 += __byte_perm(b8, 0, 0x4140); s67 += __byte_perm(b8, 0, 0x4342);
       }
-      // best cell: strict > in row-major order == max raw, lowest cell index (LL.cpp:1910-1927)
-      const uint32_t v[8] = {s01 & 0xFFFF, s01 >> 16, s23 & 0xFFFF, s23 >> 16,
-                             s45 & 0xFFFF, s45 >> 16, s67 & 0xFFFF, s67 >> 16};
-      uint32_t key = 0;
-      const int cell0 = row * 16 + half * 8;
+      if (kSplit) {
+        // the quad's partial sums meet: u16 pairs, at most 4 * 8191 per cell in total -> no carry between the halves
+        s_part[warp][lane] = make_uint4(s01, s23, s45, s67);
+        __syncthreads();
+        const int w0 = warp & ~3;
+        const uint4 a = s_part[w0][lane], b = s_part[w0 + 1][lane], cc = s_part[w0 + 2][lane], dd = s_part[w0 + 3][lane];
+        s01 = a.x + b.x + cc.x + dd.x; s23 = a.y + b.y + cc.y + dd.y;
+        s45 = a.z + b.z + cc.z + dd.z; s67 = a.w + b.w + cc.w + dd.w;
+        __syncthreads();  // before the next level / candidate overwrites the partials
+      }
+      if (kept) {
+        // best cell: strict > in row-major order == max raw, lowest cell index (LL.cpp:1910-1927)
+        const uint32_t v[8] = {s01 & 0xFFFF, s01 >> 16, s23 & 0xFFFF, s23 >> 16,
+                               s45 & 0xFFFF, s45 >> 16, s67 & 0xFFFF, s67 >> 16};
+        uint32_t key = 0;
+        const int cell0 = row * 16 + half * 8;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) key = max(key, (v[k] << 8) | (uint32_t)(255 - (cell0 + k)));
-      key = __reduce_max_sync(0xffffffffu, key);
-      const int best_raw = (int)(key >> 8);
-      int br = -1, bc = -1;
-      if (best_raw > 0) {
-        const int cell = 255 - (int)(key & 255u);
-        br = cell >> 4;
-        bc = cell & 15;
+        for (int k = 0; k < 8; ++k) key = max(key, (v[k] << 8) | (uint32_t)(255 - (cell0 + k)));
+        key = __reduce_max_sync(0xffffffffu, key);
+        const int best_raw = (int)(key >> 8);
+        int br = -1, bc = -1;
+        if (best_raw > 0) {
+          const int cell = 255 - (int)(key & 255u);
+          br = cell >> 4;
+          bc = cell & 15;
+        }
+        sim = lm_score(best_raw, nf_level);
+        x = (x / T - 8 + bc) * T + lv.off;  // LL.cpp:1930-1931
+        y = (y / T - 8 + br) * T + lv.off;
+        kept = !pruned && !(sim < p.threshold);  // remove_if(similarity < threshold), LL.cpp:1935-1937
       }
-      sim = lm_score(best_raw, nf2);
-      x = (x / T - 8 + bc) * T + lv.off;  // LL.cpp:1930-1931
-      y = (y / T - 8 + br) * T + lv.off;
-      kept = !pruned && !(sim < p.threshold);  // remove_if(similarity < threshold), LL.cpp:1935-1937
     }
-    if (lane == 0 && kept) {
+    if (lane == 0 && kept && q == 0) {
       // unordered append; (work, seq) restores the reference's pre-sort order on the host
       const int slot = atomicAdd(&p.hdr->count, 1);
       if (slot < p.capacity) {
@@ -1115,7 +1387,7 @@ __global__ void __launch_bounds__(256, LM_REFINE_MIN_CTAS) k_refine(RefineParams
       }
     }
   }
-  if (lane == 0 && feats_done) {
+  if (lane == 0 && (feats_done | rows_read)) {
     atomicAdd(p.counters + 0, (unsigned long long)feats_done);
     atomicAdd(p.counters + 1, (unsigned long long)rows_read);
   }

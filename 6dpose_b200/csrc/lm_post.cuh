@@ -30,7 +30,7 @@ struct PostParams {
   int32_t top_k;                // <= 0: every survivor (bounded by out_capacity)
   lm_match* out;                // device: survivors in pick order
   int32_t out_capacity;
-  int32_t* out_counts;          // [0] survivors written, [1] records seen, [2] survivors in total (if all were asked for)
+  int32_t* out_counts;          // [0] survivors written, [1] records seen, [2] survivors in total (if all were asked for), [3] coarse candidates
   uint8_t* live;                // [capacity] scratch
 };
 
@@ -139,5 +139,6 @@ __global__ void __launch_bounds__(1024) k_post_nms(PostParams p) {
     p.out_counts[0] = picked;
     p.out_counts[1] = p.hdr->count;
     p.out_counts[2] = p.top_k > 0 ? -1 : survivors;
+    p.out_counts[3] = p.hdr->coarse_candidates;  // the host checks it against the candidate list's capacity
   }
 }

@@ -197,17 +197,20 @@ int lm_debug_quantized(lm_detector* d, int level, int modality, uint8_t* out, in
 int lm_debug_linear_memories(lm_detector* d, int level, int modality, uint8_t* out, int64_t cap);
 /* Counters of the last lm_run: [0] templates scanned, [1] coarse candidates, [2] algorithmic bytes of
  * the coarse scan (sum over templates, modalities of features x positions),
- * [3] algorithmic bytes of the refinement (features x 256 per refined candidate and level),
- * [4] records kept after refinement, [5] bytes the refinement kernel actually read (it stops early,
- * exactly, on candidates that can no longer reach the threshold).  [0],[2] describe this handle's
- * shard.  `out6` has 6 entries. */
-int lm_counters(lm_detector* d, int64_t* out6);
+ * [3] algorithmic bytes of the refinement (features x 256 per refined candidate and level: the reference's work,
+ * whichever kernel disposed of the candidate), [4] records kept after refinement, [5] bytes of the byte linear
+ * memories the exact refinement kernel read (it stops early, exactly, on candidates that can no longer reach the
+ * threshold), [6] the part of [3] that belongs to candidates the bit-sliced upper-bound filter dropped,
+ * [7] bytes of H-planes that filter read.  [0],[2] describe this handle's shard.  `out8` has 8 entries. */
+int lm_counters(lm_detector* d, int64_t* out8);
 /* Per-stage device time in microseconds, from CUDA events recorded on the detector's stream around
- * each stage: [0] linear memories, [1] coarse scan, [2] candidate offsets, [3] refinement, [4] total.
+ * each stage: [0] linear memories, [1] coarse scan, [2] candidate offsets, [3] refinement (= [5] + [6] + [7]),
+ * [4] total, [5] candidate list + filter planes, [6] upper-bound filter, [7] exact refinement of the survivors (+ the
+ * collector of the multi-GPU exchange).
  * lm_set_timing(d, slots) with slots > 0 enables it and keeps the last `slots` runs (0 disables);
- * lm_stage_times synchronises and returns the mean over the recorded runs. */
+ * lm_stage_times synchronises and returns the mean over the recorded runs.  `out8` has 8 entries. */
 int lm_set_timing(lm_detector* d, int slots);
-int lm_stage_times(lm_detector* d, float* out5);
+int lm_stage_times(lm_detector* d, float* out8);
 /* The CUDA stream all work of this handle is issued on (cudaStream_t as void*). */
 void* lm_stream(lm_detector* d);
 /* Number of kernel launches issued by this handle since creation. */
