@@ -118,9 +118,22 @@ struct lm_detector {
   // refinement filter (k_refine_filter) on the first refined level lr = L - 2: column-major H-planes + descriptors
   bool filter_on = true;             // LINEMOD_B200_FILTER=0 switches it off (profiling / A-B runs)
   bool filter_ok = false;            // the current frame size / bank allow it
+  bool planes_direct = true;         // LINEMOD_B200_PLANES_DIRECT=0: K1 always writes byte linear memories, k_refine_prep derives the planes
+  int last_planes_level = -1;        // level the last K1 built in planes mode (its byte linear memories are stale)
+  bool bits_exact = true;            // LINEMOD_B200_BITS_EXACT=0: survivors go to the byte-wise k_refine instead
+  int filter_variant = 0;            // 0: warp per candidate (k_refine_filter_w), 1: 8 lanes per candidate (k_refine_filter)
   uint32_t* d_rp = nullptr; size_t rp_words = 0; int rp_nyb = 0;
-  uint32_t* d_rdesc = nullptr;       // per feature of level lr, grouped per template
+  uint32_t* d_rdesc = nullptr;       // per feature of level lr, grouped per template, padded to multiples of 32
+  uint8_t* d_rlab = nullptr;         // label per descriptor (8 = padding): k_refine_bits derives the neighbour planes
+  bool shard_all_eligible = false;   // every template of the shard is taken by the filter (no byte-wise refinement)
+  uint32_t* d_surv2 = nullptr;       // candidates of the templates the filter does not take
   int2* d_rfeat = nullptr;           // per template: first descriptor, count
+  std::vector<int2> h_rfeat;
+  int4* d_finfo = nullptr;           // per work item of the shard: first descriptor, count, width | height << 16,
+                                     // flags | need << 8 (need: for the threshold of the call, see filter_thresholds)
+  std::vector<int4> h_finfo;         // .w = flags only
+  std::vector<int4> h_finfo_up;      // upload staging
+  bool finfo_valid = false; float finfo_threshold = 0.f;
   uint2* d_cand = nullptr; int64_t cand_cap = 0;   // ordered candidate list (k_refine_prep)
   int64_t cand_need = 0;             // candidates of a frame that overflowed the list
   uint32_t* d_surv = nullptr;        // survivors of the filter [cand_cap]
@@ -254,6 +267,12 @@ extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** o
   {
     const char* f = getenv("LINEMOD_B200_FILTER");
     d->filter_on = !(f && f[0] == '0');
+    const char* fpd = getenv("LINEMOD_B200_PLANES_DIRECT");
+    d->planes_direct = !(fpd && fpd[0] == '0');
+    const char* fb = getenv("LINEMOD_B200_BITS_EXACT");
+    d->bits_exact = !(fb && fb[0] == '0');
+    const char* fv = getenv("LINEMOD_B200_FILTER_VARIANT");
+    d->filter_variant = (fv && fv[0] == '1') ? 1 : 0;
   }
   *out = d;
   return LM_OK;
@@ -285,6 +304,7 @@ extern "C" void lm_destroy(lm_detector* d) {
   cudaFree(d->d_items_bits); cudaFree(d->d_items_bytes); cudaFree(d->d_safe); cudaFree(d->d_galign);
   cudaFree(d->d_mask); cudaFree(d->d_raw); cudaFree(d->d_cnt); cudaFree(d->d_off);
   cudaFree(d->d_res_own); cudaFree(d->d_counters);
+  cudaFree(d->d_finfo); cudaFree(d->d_rlab); cudaFree(d->d_surv2);
   cudaFree(d->d_rp); cudaFree(d->d_rdesc); cudaFree(d->d_rfeat); cudaFree(d->d_cand); cudaFree(d->d_surv); cudaFree(d->d_queue);
   cudaFreeHost(d->h_counters); cudaFreeHost(d->h_res);
   cudaFree(d->d_post_info); cudaFree(d->d_post_out); cudaFree(d->d_post_counts); cudaFree(d->d_post_live);
@@ -557,6 +577,7 @@ static int prepare_bank(lm_detector* d) {
   // bit 1 of their flag byte; the others go to k_refine unfiltered.
   d->filter_ok = false;
   std::vector<uint32_t> rdesc;
+  std::vector<uint8_t> rlab;
   std::vector<int2> rfeat((size_t)d->G, make_int2(0, 0));
   if (d->filter_on && d->L >= 2) {
     const int lr = d->L - 2;
@@ -564,14 +585,17 @@ static int prepare_bank(lm_detector* d) {
     const int T = lv.T, T2 = T * T;
     const int nyb = lv.Hd >= 16 ? ((lv.Hd - 16) >> 4) + 1 : 0;
     const size_t words = (size_t)d->M * 8 * T2 * nyb * lv.Wd;
-    if (lv.Wd % 4 == 0 && lv.Wd >= 16 && lv.Hd >= 16 && lv.Hd <= 512 && words > 0 && words <= (1u << 23)) {
+    // all-zero tail behind the planes: where the padding descriptors (and nothing else) point
+    const size_t tail = (size_t)(nyb + 1) * lv.Wd + 64;
+    if (lv.Wd % 4 == 0 && lv.Wd >= 16 && lv.Hd >= 16 && lv.Hd <= 512 && words > 0 && words + tail <= (1u << 23)) {
       d->filter_ok = true;
       d->rp_nyb = nyb;
       if (words != d->rp_words) {
         cudaFree(d->d_rp);
         d->d_rp = nullptr;
         d->rp_words = words;
-        CU(cudaMalloc(&d->d_rp, words * 4));
+        CU(cudaMalloc(&d->d_rp, (words + tail) * 4));
+        CU(cudaMemsetAsync(d->d_rp, 0, (words + tail) * 4, d->stream));  // halves no row block covers stay zero
       }
       for (int g = 0; g < d->G; ++g) {
         int nfl = 0;
@@ -585,14 +609,23 @@ static int prepare_bank(lm_detector* d) {
             const int32_t* f = &d->feats[3 * ((size_t)tm[2] + k)];
             const uint32_t pb = (uint32_t)((m * 8 + f[2]) * T2 + (f[1] % T) * T + (f[0] % T));
             rdesc.push_back((pb * (uint32_t)nyb * (uint32_t)lv.Wd + (uint32_t)(f[0] / T)) | ((uint32_t)(f[1] / T) << 23));
+            rlab.push_back((uint8_t)f[2]);
           }
+        }
+        while (rdesc.size() % 32) {  // padding: the zero tail, row 0
+          rdesc.push_back((uint32_t)words);
+          rlab.push_back(8);
         }
       }
     }
   }
+  d->h_rfeat = rfeat;
   cudaFree(d->d_rdesc); d->d_rdesc = nullptr;
   cudaFree(d->d_rfeat); d->d_rfeat = nullptr;
+  cudaFree(d->d_rlab); d->d_rlab = nullptr;
   if (d->filter_ok) {
+    CU(cudaMalloc(&d->d_rlab, std::max<size_t>(rlab.size(), 1)));
+    if (!rlab.empty()) CU(cudaMemcpyAsync(d->d_rlab, rlab.data(), rlab.size(), cudaMemcpyHostToDevice, d->stream));
     CU(cudaMalloc(&d->d_rdesc, std::max<size_t>(rdesc.size(), 1) * 4));
     CU(cudaMalloc(&d->d_rfeat, std::max<size_t>(rfeat.size(), 1) * sizeof(int2)));
     if (!rdesc.empty()) CU(cudaMemcpyAsync(d->d_rdesc, rdesc.data(), rdesc.size() * 4, cudaMemcpyHostToDevice, d->stream));
@@ -652,6 +685,23 @@ static int prepare_work(lm_detector* d) {
     CU(cudaMalloc(&d->d_cnt, sizeof(int32_t) * d->cnt_elems));
     CU(cudaMalloc(&d->d_off, sizeof(int32_t) * d->cnt_elems));
   }
+  cudaFree(d->d_finfo);
+  d->d_finfo = nullptr;
+  d->h_finfo.clear();
+  if (d->filter_ok && n > 0) {
+    const int lr = d->L - 2;
+    d->h_finfo.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+      const int g = d->shard_sel[(size_t)i];
+      const int32_t* t0 = &d->tmeta[((size_t)g * d->S + lr * d->M) * 4];
+      d->h_finfo[(size_t)i] = make_int4(d->h_rfeat[(size_t)g].x, d->h_rfeat[(size_t)g].y,
+                                        (int)((uint32_t)t0[0] | ((uint32_t)t0[1] << 16)), (int)d->safe[(size_t)g]);
+    }
+    CU(cudaMalloc(&d->d_finfo, sizeof(int4) * (size_t)n));
+    d->finfo_valid = false;  // the threshold-dependent part is filled in by lm_enqueue
+    d->shard_all_eligible = true;
+    for (const int4& f : d->h_finfo) d->shard_all_eligible = d->shard_all_eligible && (f.w & 2);
+  }
   // per-template candidate counts are accumulated with atomics and re-zeroed by k_scan_counts
   CU(cudaMemsetAsync(d->d_cnt, 0, sizeof(int32_t) * d->cnt_elems, d->stream));
   CU(cudaStreamSynchronize(d->stream));
@@ -670,6 +720,41 @@ static int prepare_work(lm_detector* d) {
   }
   d->alg_scan_bytes = bytes;
   d->work_dirty = false;
+  return LM_OK;
+}
+
+// Smallest raw score that survives remove_if(similarity < threshold) (LL.cpp:1935-1937), host twin of lm_min_kept_raw:
+// the same two IEEE single-precision operations ((raw * 100.f) / (4 * n)).
+static int host_min_kept_raw(float threshold, int nfeat) {
+  int lo = 0, hi = 4 * nfeat + 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    volatile float prod = (float)mid * 100.f;
+    volatile float score = prod / (float)(4 * nfeat);
+    if (!(score < threshold)) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// finfo[w].w = flags | need << 8 for this threshold: need = number of features whose label bit must be set at some cell
+// of the patch for the candidate to be able to reach raw_keep (see k_refine_filter).
+static int filter_thresholds(lm_detector* d, float threshold) {
+  if (!d->filter_ok || !d->d_finfo || d->h_finfo.empty()) return LM_OK;
+  if (d->finfo_valid && memcmp(&threshold, &d->finfo_threshold, sizeof(float)) == 0) return LM_OK;
+  d->h_finfo_up = d->h_finfo;
+  int last_nf = -1, last_need = 0;
+  for (int4& f : d->h_finfo_up) {
+    if (!(f.w & 2)) continue;
+    if (f.y != last_nf) {
+      last_nf = f.y;
+      const int over = host_min_kept_raw(threshold, f.y) - f.y;
+      last_need = over > 0 ? (over + 2) / 3 : 0;
+    }
+    f.w |= last_need << 8;
+  }
+  CU(cudaMemcpyAsync(d->d_finfo, d->h_finfo_up.data(), sizeof(int4) * d->h_finfo_up.size(), cudaMemcpyHostToDevice, d->stream));
+  d->finfo_valid = true;
+  d->finfo_threshold = threshold;
   return LM_OK;
 }
 
@@ -891,6 +976,88 @@ static LevelDev level_dev(const LevelHost& h) {
 }
 
 
+// K1 launch plan: block ranges per level (lowest level first), kernel variant and shared memory.  planes_level >= 0: that
+// level is built in planes mode (column-major H-planes only, no byte linear memories; see spread_planes_block).
+struct K1Plan {
+  LinMemParams p;
+  bool band = false;
+  size_t smem = 0;
+  int blocks = 0;
+};
+
+static void plan_k1(lm_detector* d, int planes_level, bool with_bit_planes, K1Plan& k) {
+  LinMemParams& p = k.p;
+  memset(&p, 0, sizeof(p));
+  p.L = d->L; p.M = d->M; p.block_offset = 0;
+  bool band = true;
+  size_t smem = 0;
+  for (int l = 0; l < d->L; ++l) {
+    const LevelHost& lv = d->lv[l];
+    band = band && (lv.cols % 4 == 0) && (lv.Wd % 4 == 0) && (lv.plane % 4 == 0);
+    // the most segments (a divisor of Wd / 4, so that a segment keeps a multiple of 4 positions) that still
+    // leave every thread of the CTA one 4-position group of one grid: equal, light CTAs on every level
+    int nseg = 1;
+    if (lv.Wd % 4 == 0)
+      for (int j = 1; j <= 16 && j <= lv.Wd / 4; ++j)
+        if ((lv.Wd / 4) % j == 0 && (lv.T * lv.T * (lv.Wd / 4)) / j >= 128) nseg = j;
+    p.lv[l].nseg = nseg;
+    const size_t wp = (size_t)((lv.Wd / nseg * lv.T + lv.T + 3 + 4) & ~3);
+    size_t need = wp * (size_t)(2 * (2 * lv.T - 1) + lv.T);
+    if (l == planes_level) {
+      // positions per segment: T*T * pseg = one (grid, column) item per thread of the 128-thread CTA where possible
+      int pseg = 4;
+      for (int c : {32, 16, 8})
+        if (lv.Wd % c == 0 && lv.T * lv.T * c <= 128) { pseg = c; break; }
+      if (const char* e = getenv("LINEMOD_B200_PSEG")) { const int v = atoi(e); if (v >= 4 && v % 4 == 0 && lv.Wd % v == 0) pseg = v; }
+      p.lv[l].pseg = pseg;
+      const size_t wpp = (size_t)((pseg * lv.T + lv.T + 3 + 4) & ~3);
+      need = wpp * (size_t)(2 * (16 * lv.T + lv.T - 1) + 16 * lv.T);
+    }
+    smem = std::max(smem, need);
+  }
+  band = band && smem <= LM_BAND_SMEM_LIMIT;
+  int blocks = 0;
+  // block index order = lowest level first: its CTAs are the heavy ones (T*T = 64 grids per position row plus
+  // the bit-plane atomics), started last they would be the tail of the launch
+  for (int l = d->L - 1; l >= 0; --l) {
+    const LevelHost& lv = d->lv[l];
+    LinMemLevel& q = p.lv[l];
+    for (int m = 0; m < d->M; ++m) q.q[m] = lv.q_src[m];
+    q.lm = lv.d_lm; q.bp = with_bit_planes ? lv.d_bp : nullptr; q.lbw = lv.lbw;
+    q.T = lv.T; q.rows = lv.rows; q.cols = lv.cols; q.Wd = lv.Wd; q.Hd = lv.Hd; q.plane = lv.plane;
+    q.mod_stride = lv.mod_stride;
+    q.rp = nullptr; q.nyb = 0;
+    if (band && l == planes_level) {
+      q.rp = d->d_rp; q.nyb = d->rp_nyb;
+      blocks += ((lv.Hd + 15) / 16) * (lv.Wd / q.pseg);
+    } else {
+      blocks += band ? lv.Hd * q.nseg : (lv.T * lv.T * lv.plane + 255) / 256;
+    }
+    q.block_end = blocks;
+  }
+  k.band = band;
+  k.smem = smem;
+  k.blocks = blocks;
+}
+
+static int launch_k1(lm_detector* d, const K1Plan& k, int first_block, int n_blocks) {
+  if (n_blocks <= 0) return LM_OK;
+  LinMemParams p = k.p;
+  p.block_offset = first_block;
+  if (k.band) CU(launch_pdl(k_linear_memories_band, dim3((unsigned)n_blocks, (unsigned)d->M), dim3(128), k.smem, d->stream, p));
+  else CU(launch_pdl(k_linear_memories, dim3((unsigned)n_blocks, (unsigned)d->M), dim3(256), 0, d->stream, p));
+  ++d->launches;
+  return LM_OK;
+}
+
+// Which refinement path the current bank / shard / frame size take (see enqueue_stages).
+static bool use_filter(const lm_detector* d) { return d->filter_ok && d->d_rp != nullptr && d->d_finfo != nullptr; }
+static bool use_bits(const lm_detector* d) { return use_filter(d) && d->L == 2 && d->filter_variant == 0 && d->bits_exact; }
+// level built in planes mode by K1, or -1: only when nothing reads that level's byte linear memories
+static int planes_level(const lm_detector* d) {
+  return (use_bits(d) && d->shard_all_eligible && d->planes_direct) ? d->L - 2 : -1;
+}
+
 // Enqueue every GPU stage of one frame on the detector's stream; no host synchronisation.
 static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
   const int n_work = (int)d->shard_count;
@@ -911,60 +1078,18 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     d->ev = d->tev.data() + LM_TEV * (size_t)(d->timing_runs % (int64_t)(d->tev.size() / LM_TEV));
     ++d->timing_runs;
   }
-  LinMemParams k1;
-  bool k1_band = false;
-  size_t k1_smem = 0;
-  int k1_blocks = 0, k1_done = 0;
+  K1Plan k1;
+  int k1_done = 0;
   if (!refine_only) {
     if (d->timing) CU(cudaEventRecord(d->ev[0], st));
-    // K1: one launch for every level and modality
-    {
-      LinMemParams p;
-      p.L = d->L; p.M = d->M; p.block_offset = 0;
-      bool band = true;
-      size_t smem = 0;
-      for (int l = 0; l < d->L; ++l) {
-        const LevelHost& lv = d->lv[l];
-        band = band && (lv.cols % 4 == 0) && (lv.Wd % 4 == 0) && (lv.plane % 4 == 0);
-        // column segments: as many as keep a multiple of 4 positions per segment (more CTAs in flight)
-        // the most segments (a divisor of Wd / 4, so that a segment keeps a multiple of 4 positions) that still
-        // leave every thread of the CTA one 4-position group of one grid: equal, light CTAs on every level
-        int nseg = 1;
-        if (lv.Wd % 4 == 0)
-          for (int k = 1; k <= 16 && k <= lv.Wd / 4; ++k)
-            if ((lv.Wd / 4) % k == 0 && (lv.T * lv.T * (lv.Wd / 4)) / k >= 128) nseg = k;
-        p.lv[l].nseg = nseg;
-        const size_t wp = (size_t)((lv.Wd / nseg * lv.T + lv.T + 3 + 4) & ~3);
-        smem = std::max(smem, wp * (size_t)(2 * (2 * lv.T - 1) + lv.T));
-      }
-      band = band && smem <= LM_BAND_SMEM_LIMIT;
-      int blocks = 0;
-      // block index order = lowest level first: its CTAs are the heavy ones (T*T = 64 grids per position row plus
-      // the bit-plane atomics), started last they would be the tail of the launch
-      for (int l = d->L - 1; l >= 0; --l) {
-        const LevelHost& lv = d->lv[l];
-        LinMemLevel& q = p.lv[l];
-        for (int m = 0; m < d->M; ++m) q.q[m] = lv.q_src[m];
-        q.lm = lv.d_lm; q.bp = lv.d_bp; q.lbw = lv.lbw;
-        q.T = lv.T; q.rows = lv.rows; q.cols = lv.cols; q.Wd = lv.Wd; q.Hd = lv.Hd; q.plane = lv.plane;
-        q.mod_stride = lv.mod_stride;
-        blocks += band ? lv.Hd * q.nseg : (lv.T * lv.T * lv.plane + 255) / 256;
-        q.block_end = blocks;
-      }
-      // bit-planes are OR-ed in: zero at allocation, re-zeroed by k_refine after every frame.
-      // With a host upload in flight (upper levels still on the copy stream) the launch is split: the lowest
-      // level now, the levels above it behind the coarse scan, once their images have landed.
-      k1 = p;
-      k1_band = band;
-      k1_smem = smem;
-      k1_blocks = blocks;
-      const int first_n = d->upper_pending ? p.lv[d->L - 1].block_end : blocks;
-      k1_done = first_n;
-      p.block_offset = 0;
-      if (band) CU(launch_pdl(k_linear_memories_band, dim3((unsigned)first_n, (unsigned)d->M), dim3(128), smem, st, p));
-      else CU(launch_pdl(k_linear_memories, dim3((unsigned)first_n, (unsigned)d->M), dim3(256), 0, st, p));
-      ++d->launches;
-    }
+    // K1: one launch for every level and modality.  Bit-planes are OR-ed in: zero at allocation, re-zeroed by the
+    // refinement kernel after every frame.  With a host upload in flight (upper levels still on the copy stream) the
+    // launch is split: the lowest level now, the levels above it behind the coarse scan, once their images have landed.
+    plan_k1(d, planes_level(d), true, k1);
+    d->last_planes_level = k1.band ? planes_level(d) : -1;
+    k1_done = d->upper_pending ? k1.p.lv[d->L - 1].block_end : k1.blocks;
+    int rc1 = launch_k1(d, k1, 0, k1_done);
+    if (rc1) return rc1;
     if (d->timing) CU(cudaEventRecord(d->ev[1], st));
     // K2
     bool scan_fused = false;
@@ -1028,13 +1153,10 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       ++d->launches;
     }
     if (d->timing) CU(cudaEventRecord(d->ev[3], st));
-    if (k1_done < k1_blocks) {  // the upper levels' linear memories, behind their images
+    if (k1_done < k1.blocks) {  // the upper levels' linear memories, behind their images
       CU(cudaStreamWaitEvent(st, d->ev_upper, 0));
-      k1.block_offset = k1_done;
-      const unsigned nb = (unsigned)(k1_blocks - k1_done);
-      if (k1_band) CU(launch_pdl(k_linear_memories_band, dim3(nb, (unsigned)d->M), dim3(128), k1_smem, st, k1));
-      else CU(launch_pdl(k_linear_memories, dim3(nb, (unsigned)d->M), dim3(256), 0, st, k1));
-      ++d->launches;
+      int rc2 = launch_k1(d, k1, k1_done, k1.blocks - k1_done);
+      if (rc2) return rc2;
     }
     d->upper_pending = false;
   }
@@ -1043,7 +1165,9 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     CU(cudaMemsetAsync(d->d_queue, 0, 4 * sizeof(int), st));
     CU(cudaMemsetAsync(&d->d_res->count, 0, sizeof(int32_t), st));
   }
-  const bool filter = d->filter_ok && d->d_rp != nullptr;
+  const bool filter = use_filter(d);
+  // two pyramid levels: the filtered level is the last one, its survivors are finished bit-sliced (k_refine_bits)
+  const bool bits_mode = use_bits(d);
   const LevelHost& lref = d->lv[d->L >= 2 ? d->L - 2 : 0];
   {
     // ordered candidate list (+ the filter's H-planes of the first refined level)
@@ -1052,10 +1176,10 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     pp.n_work = n_work; pp.nwords = low.nwords;
     pp.cand = d->d_cand; pp.cand_cap = (int)d->cand_cap;
     pp.expand_blocks = std::max(1, std::min((n_work + 7) / 8, d->sm_count * 8));
-    pp.lm = lref.d_lm; pp.rp = filter ? d->d_rp : nullptr;
+    pp.lm = lref.d_lm; pp.rp = (filter && d->last_planes_level < 0) ? d->d_rp : nullptr;  // else: K1 wrote the planes
     pp.Wd = lref.Wd; pp.Hd = lref.Hd; pp.plane = lref.plane; pp.nyb = d->rp_nyb;
     pp.n_pb = d->M * 8 * lref.T * lref.T;
-    const int plane_blocks = filter ? (int)(((size_t)pp.n_pb * pp.nyb * (pp.Wd / 4) + 255) / 256) : 0;
+    const int plane_blocks = pp.rp ? (int)(((size_t)pp.n_pb * pp.nyb * (pp.Wd / 4) + 255) / 256) : 0;
     CU(launch_pdl(k_refine_prep, dim3((unsigned)(pp.expand_blocks + plane_blocks)), dim3(256), 0, st, pp));
     ++d->launches;
   }
@@ -1063,23 +1187,46 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
   if (filter) {
     FilterParams fp;
     fp.rp = d->d_rp; fp.Wd = lref.Wd; fp.nyb = d->rp_nyb;
-    fp.rdesc = d->d_rdesc; fp.rfeat = d->d_rfeat; fp.flags = d->d_safe;
+    fp.rdesc = d->d_rdesc; fp.rfeat = d->d_rfeat; fp.finfo = d->d_finfo; fp.flags = d->d_safe;
     fp.tslot = d->d_tslot; fp.work = d->d_work; fp.S = d->S; fp.M = d->M; fp.L = d->L;
     fp.low = level_dev(low); fp.ref = level_dev(lref);
     fp.cand = d->d_cand; fp.off = d->d_off; fp.n_work = n_work; fp.cand_cap = (int)d->cand_cap;
     fp.threshold = threshold;
-    fp.surv = d->d_surv; fp.queue = d->d_queue; fp.counters = d->d_counters;
-    CU(launch_pdl(k_refine_filter, dim3((unsigned)(d->sm_count * 4)), dim3(256), 0, st, fp));
+    fp.surv = d->d_surv; fp.surv2 = bits_mode ? d->d_surv2 : nullptr; fp.queue = d->d_queue; fp.counters = d->d_counters;
+    if (d->filter_variant == 0) CU(launch_pdl(k_refine_filter_w, dim3((unsigned)(d->sm_count * LM_FILTER_MIN_CTAS)), dim3(256), 0, st, fp));
+    else CU(launch_pdl(k_refine_filter, dim3((unsigned)(d->sm_count * 4)), dim3(256), 0, st, fp));
     ++d->launches;
   }
   if (d->timing && !refine_only) CU(cudaEventRecord(d->ev[5], st));
-  {
+  const bool bytes_pass = !bits_mode || !d->shard_all_eligible;  // byte-wise exact refinement needed for this shard
+  if (bits_mode) {
+    // exact refinement of the survivors, bit-sliced, from the same H-planes
+    RefineBitsParams bq;
+    bq.rp = d->d_rp; bq.Wd = lref.Wd; bq.label_stride = lref.T * lref.T * d->rp_nyb * lref.Wd;
+    bq.rdesc = d->d_rdesc; bq.rlab = d->d_rlab; bq.finfo = d->d_finfo;
+    bq.low = level_dev(low); bq.ref = level_dev(lref);
+    bq.cand = d->d_cand; bq.off = d->d_off; bq.n_work = n_work; bq.cand_cap = (int)d->cand_cap;
+    bq.surv = d->d_surv; bq.queue = d->d_queue;
+    bq.threshold = threshold;
+    bq.work_begin = (int)d->work_base; bq.work_stride = (int)d->work_stride;
+    bq.hdr = px.world > 0 ? px_block : d->d_res;
+    bq.capacity = (int32_t)(px.world > 0 ? d->px_cap : d->res_cap);
+    bq.px = px.world > 0 ? d->d_px : nullptr; bq.px_seq = d->px_seq;
+    bq.publish = bytes_pass ? 0 : 1;
+    bq.counters = d->d_counters;
+    bq.bp_clear = low.d_bp; bq.bp_words = low.d_bp ? (uint32_t)((size_t)d->M * 8 * low.lbw) : 0u;
+    CU(launch_pdl(k_refine_bits, dim3((unsigned)(d->sm_count * 6)), dim3(256), 0, st, bq));
+    ++d->launches;
+  }
+  if (bytes_pass) {
     // persistent grid: the candidate total is read on the device (no host round trip)
     RefineParams rp;
     for (int l = 0; l < d->L; ++l) rp.lv[l] = level_dev(d->lv[l]);
     rp.tslot = d->d_tslot; rp.fbase = d->d_fbase; rp.fxy = d->d_fxy; rp.work = d->d_work;
     rp.off = d->d_off; rp.cand = d->d_cand; rp.cand_cap = (int)d->cand_cap; rp.raw = d->d_raw;
-    rp.surv = filter ? d->d_surv : nullptr; rp.queue = d->d_queue;
+    rp.surv = filter ? (bits_mode ? d->d_surv2 : d->d_surv) : nullptr; rp.queue = d->d_queue;
+    rp.surv_slot = bits_mode ? 2 : 1;
+    rp.publish = 1;
     rp.n_work = n_work; rp.L = d->L; rp.S = d->S; rp.M = d->M;
     rp.work_begin = (int)d->work_base;
     rp.work_stride = (int)d->work_stride;
@@ -1093,7 +1240,8 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     }
     rp.counters = d->d_counters;
     rp.safe = d->d_safe; rp.galign = d->d_galign;
-    rp.bp_clear = low.d_bp; rp.bp_words = low.d_bp ? (uint32_t)((size_t)d->M * 8 * low.lbw) : 0u;
+    rp.bp_clear = bits_mode ? nullptr : low.d_bp;
+    rp.bp_words = (!bits_mode && low.d_bp) ? (uint32_t)((size_t)d->M * 8 * low.lbw) : 0u;
     // 4 CTAs are resident per SM (64 registers x 256 threads); 16 per SM = four waves of equal shares, which
     // balances the very uneven per-candidate cost (row-wise early exit) better than one persistent wave
     // (measured: 4 -> 251 us, 8 -> 241, 12..32 -> 229)
@@ -1148,11 +1296,12 @@ static int ensure_run_buffers(lm_detector* d) {
     const int64_t worst = std::max<int64_t>(n_work, 1) * low.plane;
     const int64_t want = std::min<int64_t>(worst, std::max<int64_t>(LM_CAND_DEFAULT, d->cand_need));
     if (want > d->cand_cap) {
-      cudaFree(d->d_cand); cudaFree(d->d_surv);
-      d->d_cand = nullptr; d->d_surv = nullptr;
+      cudaFree(d->d_cand); cudaFree(d->d_surv); cudaFree(d->d_surv2);
+      d->d_cand = nullptr; d->d_surv = nullptr; d->d_surv2 = nullptr;
       d->cand_cap = want;
       CU(cudaMalloc(&d->d_cand, sizeof(uint2) * (size_t)want));
       CU(cudaMalloc(&d->d_surv, sizeof(uint32_t) * (size_t)want));
+      CU(cudaMalloc(&d->d_surv2, sizeof(uint32_t) * (size_t)want));
     }
   }
   if (d->px_rank >= 0 && d->res_external) return fail(LM_E_STATE, "lm_set_result_buffer and a connected peer exchange exclude each other");
@@ -1230,6 +1379,8 @@ extern "C" int lm_enqueue(lm_detector* d, float threshold) {
   rc = ensure_run_buffers(d);
   if (rc) return rc;
   d->last_threshold = threshold;
+  rc = filter_thresholds(d, threshold);
+  if (rc) return rc;
   return enqueue_stages(d, threshold, false);
 }
 
@@ -1768,6 +1919,16 @@ extern "C" int lm_debug_linear_memories(lm_detector* d, int level, int modality,
   const LevelHost& lv = d->lv[level];
   if ((int64_t)lv.mod_stride > cap) return fail(LM_E_CAPACITY, "need %u bytes", lv.mod_stride);
   CU(cudaSetDevice(d->device));
+  if (level == d->last_planes_level) {
+    // the last run built this level as H-planes only (nothing reads its bytes): build the bytes now, from the frame that
+    // is still bound, without touching the bit-planes
+    K1Plan k;
+    plan_k1(d, -1, false, k);
+    const int b0 = level == d->L - 1 ? 0 : k.p.lv[level + 1].block_end;
+    int rc = launch_k1(d, k, b0, k.p.lv[level].block_end - b0);
+    if (rc) return rc;
+    d->last_planes_level = -1;
+  }
   CU(cudaMemcpyAsync(out, lv.d_lm + (size_t)modality * lv.mod_stride, lv.mod_stride, cudaMemcpyDeviceToHost, d->stream));
   CU(cudaStreamSynchronize(d->stream));
   return LM_OK;

@@ -81,6 +81,11 @@ struct LinMemLevel {
   uint32_t mod_stride;
   int block_end;  // blocks [previous end, block_end) of the launch belong to this level (per modality)
   int nseg;       // band kernel: column segments per row of positions (Wd / nseg is a multiple of 4)
+  // planes mode (band kernel): instead of the byte linear memories the level gets ONLY the column-major H-planes the
+  // bit-sliced refinement reads (k_refine_filter_w / k_refine_bits), straight from the spread masks
+  uint32_t* rp;   // non-null: planes mode
+  int nyb;        // words per column: word yb = rows 16*yb .. 16*yb + 31
+  int pseg;       // positions per column segment of a planes-mode CTA
 };
 
 struct LinMemParams {
@@ -254,6 +259,105 @@ __device__ __forceinline__ void linear_memories_band_level(const LinMemLevel& lv
   }
 }
 
+// K1, planes mode: one CTA per (level, modality, block of 16 rows of positions, column segment).  The 16*T (+ T-1) image
+// rows are staged and OR-spread exactly as in the band version; then thread (grid, column) walks its 16 positions down the
+// block and packs, per label, their H bits into a 16-bit half: the low half of word yb = block and the high half of word
+// yb - 1 (words overlap by 16 rows, see k_refine_prep) -- plain 16-bit stores, no atomics, nothing to clear.
+template <int TT>
+__device__ __forceinline__ void spread_planes_block(const LinMemLevel& lv, int m, int bi, uint8_t* s_band) {
+  const int T = TT > 0 ? TT : lv.T;
+  const int nsegp = lv.Wd / lv.pseg;
+  const int rb = bi / nsegp, seg = bi - rb * nsegp;
+  const int cols = lv.cols, rows = lv.rows;
+  const int Wseg = lv.pseg;
+  const int x0 = seg * Wseg * T;
+  const int cseg = Wseg * T;
+  const int Wp = (cseg + T + 3 + 4) & ~3;
+  const int nrow = 16 * T;         // image rows that hold the block's positions
+  const int nin = nrow + T - 1;    // + the forward window
+  uint8_t* s_in = s_band;          // [nin][Wp]
+  uint8_t* s_h = s_in + nin * Wp;  // [nin][Wp] horizontal OR
+  uint8_t* s_sp = s_h + nin * Wp;  // [nrow][Wp] spread masks
+  const uint8_t* __restrict__ q = (m == 0) ? lv.q[0] : lv.q[1];
+  const int y0 = rb * nrow;
+  const int wpr = Wp >> 2, cw = cseg >> 2;
+  const int nthr = blockDim.x;
+  {
+    // 16*T + T-1 rows: eight loads in flight per thread (one round trip to the frame, not one per row)
+    const int n = nin * wpr;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * nthr) {
+      uint32_t v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + k * nthr;
+        const int r = i / wpr, c = i - r * wpr;
+        v[k] = 0u;
+        if (i < n && x0 + 4 * c < cols && y0 + r < rows)
+          v[k] = __ldg(reinterpret_cast<const uint32_t*>(q + (size_t)(y0 + r) * cols + x0) + c);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (i0 + k * nthr < n) reinterpret_cast<uint32_t*>(s_in)[i0 + k * nthr] = v[k];
+    }
+  }
+  __syncthreads();
+  {
+    RowCol rc(threadIdx.x, cw);
+    for (int i = threadIdx.x; i < nin * cw; i += nthr, rc.advance(nthr, cw)) {
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(s_in + rc.r * Wp) + rc.c;
+      uint32_t acc = row[0];
+      if (TT == 4) {
+        const uint32_t n1 = row[1];
+        acc |= __funnelshift_r(row[0], n1, 8) | __funnelshift_r(row[0], n1, 16) | __funnelshift_r(row[0], n1, 24);
+      } else if (TT == 8) {
+        const uint32_t n1 = row[1], n2 = row[2];
+        acc |= __funnelshift_r(row[0], n1, 8) | __funnelshift_r(row[0], n1, 16) | __funnelshift_r(row[0], n1, 24) | n1 |
+               __funnelshift_r(n1, n2, 8) | __funnelshift_r(n1, n2, 16) | __funnelshift_r(n1, n2, 24);
+      } else {
+        for (int dx = 1; dx < T; ++dx) acc |= __funnelshift_r(row[dx >> 2], row[(dx >> 2) + 1], (dx & 3) << 3);
+      }
+      reinterpret_cast<uint32_t*>(s_h + rc.r * Wp)[rc.c] = acc;
+    }
+  }
+  __syncthreads();
+  {
+    RowCol rc(threadIdx.x, cw);
+    for (int i = threadIdx.x; i < nrow * cw; i += nthr, rc.advance(nthr, cw)) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int dy = 0; dy < (TT > 0 ? TT : 1); ++dy) acc |= reinterpret_cast<const uint32_t*>(s_h + (rc.r + dy) * Wp)[rc.c];
+      if (TT == 0)
+        for (int dy = 1; dy < T; ++dy) acc |= reinterpret_cast<const uint32_t*>(s_h + (rc.r + dy) * Wp)[rc.c];
+      reinterpret_cast<uint32_t*>(s_sp + rc.r * Wp)[rc.c] = acc;
+    }
+  }
+  __syncthreads();
+  const int T2 = T * T;
+  uint16_t* __restrict__ rp16 = reinterpret_cast<uint16_t*>(lv.rp);
+  RowCol gk(threadIdx.x, Wseg);  // r = grid, c = column of the segment
+  for (int i = threadIdx.x; i < T2 * Wseg; i += nthr, gk.advance(nthr, Wseg)) {
+    const int g = gk.r, k = gk.c;
+    const int gy = TT > 0 ? g / TT : g / T, gx = g - gy * T;
+    const uint8_t* sp = s_sp + gy * Wp + k * T + gx;
+    uint32_t half[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) half[o] = 0u;
+#pragma unroll 4
+    for (int b = 0; b < 16; ++b) {
+      const uint32_t v = sp[(size_t)b * T * Wp];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) half[o] |= ((v >> o) & 1u) << b;
+    }
+    const int x = seg * Wseg + k;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const size_t pb = (size_t)((m * 8 + o) * T2 + g);
+      if (rb < lv.nyb) rp16[((pb * lv.nyb + rb) * lv.Wd + x) * 2] = (uint16_t)half[o];
+      if (rb >= 1 && rb - 1 < lv.nyb) rp16[((pb * lv.nyb + rb - 1) * lv.Wd + x) * 2 + 1] = (uint16_t)half[o];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_linear_memories_band(LinMemParams p) {
   lm_pdl_wait();
   extern __shared__ __align__(16) uint8_t s_band[];
@@ -263,6 +367,14 @@ __global__ void __launch_bounds__(256) k_linear_memories_band(LinMemParams p) {
   while (l > 0 && bx >= p.lv[l].block_end) { first = p.lv[l].block_end; --l; }
   const LinMemLevel& lv = p.lv[l];
   const int bi = bx - first;
+  if (lv.rp) {  // planes mode
+    switch (lv.T) {
+      case 4: spread_planes_block<4>(lv, blockIdx.y, bi, s_band); break;
+      case 8: spread_planes_block<8>(lv, blockIdx.y, bi, s_band); break;
+      default: spread_planes_block<0>(lv, blockIdx.y, bi, s_band); break;
+    }
+    return;
+  }
   switch (lv.T) {  // block-uniform
     case 4: linear_memories_band_level<4>(lv, blockIdx.y, bi, s_band); break;
     case 8: linear_memories_band_level<8>(lv, blockIdx.y, bi, s_band); break;
@@ -394,8 +506,9 @@ __device__ __forceinline__ void scan_counts_block(int32_t* __restrict__ cnt, int
     counters[1] = 0ull;
     counters[4] = 0ull;  // k_refine_filter: features x candidates it dropped, plane words it read
     counters[5] = 0ull;
-    queue[0] = 0;        // k_refine_filter: next candidate, survivors appended
+    queue[0] = 0;        // k_refine_filter: next candidate, survivors appended (two lists)
     queue[1] = 0;
+    queue[2] = 0;
   }
 }
 
@@ -869,14 +982,21 @@ __global__ void __launch_bounds__(256) k_refine_prep(PrepParams p) {
   const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(p.lm + (size_t)pb * p.plane) + x4;
   uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
   const int r0 = 16 * yb;
-#pragma unroll 8
-  for (int b = 0; b < 32; ++b) {
-    const int r = r0 + b;
-    const uint32_t v = (r < p.Hd) ? __ldg(src + (size_t)r * wq) : 0u;
-    o0 |= ((v >> 2) & 1u) << b;
-    o1 |= ((v >> 10) & 1u) << b;
-    o2 |= ((v >> 18) & 1u) << b;
-    o3 |= ((v >> 26) & 1u) << b;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {  // 8 rows at a time: byte c of t collects the 8 row bits of column c
+    uint32_t v[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int r = r0 + 8 * k + b;
+      v[b] = (r < p.Hd) ? __ldg(src + (size_t)r * wq) : 0u;
+    }
+    uint32_t t = 0u;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) t += ((v[b] >> 2) & 0x01010101u) << b;  // response 4 <=> bit 2; the bits never meet
+    o0 |= (t & 0xFFu) << (8 * k);
+    o1 |= ((t >> 8) & 0xFFu) << (8 * k);
+    o2 |= ((t >> 16) & 0xFFu) << (8 * k);
+    o3 |= (t >> 24) << (8 * k);
   }
   *reinterpret_cast<uint4*>(p.rp + ((size_t)pb * p.nyb + yb) * p.Wd + 4 * x4) = make_uint4(o0, o1, o2, o3);
 }
@@ -903,6 +1023,7 @@ struct FilterParams {
   int Wd, nyb;
   const uint32_t* rdesc;   // per feature (own order, grouped per template): plane word offset incl. x / T : 23 | y / T : 9
   const int2* rfeat;       // per template: first descriptor, number of features of the level (all modalities)
+  const int4* finfo;       // per WORK ITEM of the shard: the same + width | height << 16 of the level's template + flags
   const uint8_t* flags;    // per template: bit 0 = "safe" (k_refine's fast path), bit 1 = the filter may take it
   const TSlot* tslot;
   const int32_t* work;
@@ -913,7 +1034,8 @@ struct FilterParams {
   int n_work, cand_cap;
   float threshold;
   uint32_t* surv;          // survivors (candidate indices), unordered
-  int* queue;              // [0] next candidate, [1] survivors
+  uint32_t* surv2;         // optional second list: candidates of templates the filter does not take (k_refine_filter_w)
+  int* queue;              // [0] next candidate, [1] survivors, [2] entries of surv2
   unsigned long long* counters;  // [4] features x candidates dropped here, [5] plane words read
 };
 
@@ -1061,6 +1183,166 @@ __global__ void __launch_bounds__(256, 4) k_refine_filter(FilterParams p) {
 }
 
 
+// k_refine_filter_w: the same test with ONE WARP per candidate (the default; LINEMOD_B200_FILTER_VARIANT=1 selects the
+// kernel above).  The four 8-lane groups of the warp work on the SAME 16x16 patch and deal the features between them: of
+// every 32 consecutive features group q adds features 8q .. 8q+7 into its own partial counter, so a candidate is a chain
+// of nf / 32 steps instead of nf / 8 (a chain four times shorter: what matters when the candidates are fewer than the
+// machine has lanes, e.g. a 1/8 template shard).  Lane L decodes descriptor L of the step once (word offset and shift
+// packed in one register) and the lanes of group q pick theirs up by shuffle; control flow is warp-uniform.  The partial
+// counters meet (bit-sliced adds across the groups, two butterfly steps) at two check points -- after about half and
+// three quarters of the features -- where cells, lanes and whole candidates that can no longer reach `need` are dropped,
+// and at the end.
+__device__ __forceinline__ void vc_allreduce_groups(uint32_t (&c)[LM_FILTER_BITS]) {
+#pragma unroll
+  for (int step = 8; step <= 16; step <<= 1) {
+    uint32_t carry = 0u;
+#pragma unroll
+    for (int b = 0; b < LM_FILTER_BITS; ++b) {
+      const uint32_t o = __shfl_xor_sync(0xffffffffu, c[b], step);
+      const uint32_t a = c[b];
+      c[b] = a ^ o ^ carry;
+      carry = (a & o) | (carry & (a ^ o));
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t vc_ge(const uint32_t (&c)[LM_FILTER_BITS], int thr) {
+  if (thr <= 0) return 0xffffffffu;
+  uint32_t gt = 0u, eq = 0xffffffffu;
+#pragma unroll
+  for (int b = LM_FILTER_BITS - 1; b >= 0; --b) {
+    const uint32_t tb = 0u - (((uint32_t)thr >> b) & 1u);
+    gt |= eq & c[b] & ~tb;
+    eq &= ~(c[b] ^ tb);
+  }
+  return gt | eq;
+}
+
+// base + 32-bit byte offset as ONE wide multiply-add (FMA pipe) instead of a shift-mask-add-carry chain on the ALU pipe
+__device__ __forceinline__ const uint32_t* lm_ptr_add(const char* base, uint32_t byte_off) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(byte_off), "l"(reinterpret_cast<unsigned long long>(base)));
+  return reinterpret_cast<const uint32_t*>(r);
+}
+
+#ifndef LM_FILTER_MIN_CTAS
+#define LM_FILTER_MIN_CTAS 5
+#endif
+// Layout contract with the host (prepare_bank / prepare_work): every template's descriptors are padded to a multiple of
+// 32 with descriptors that point into an all-zero tail of the plane buffer (so the loop needs no bounds predicate), and
+// finfo[w] = {first descriptor, features of the level, width | height << 16, flags | need << 8} with `need` computed on
+// the host for the call's threshold with the same two IEEE float operations (lm_min_kept_raw).
+__global__ void __launch_bounds__(256, LM_FILTER_MIN_CTAS) k_refine_filter_w(FilterParams p) {
+  lm_pdl_wait();
+  const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+  const int total = min(p.off[p.n_work], p.cand_cap);
+  const int T = p.ref.T, border = 8 * T;
+  const int Wd = p.Wd;
+  unsigned words_read = 0, dropped_feats = 0;
+  // the NEXT candidate's index, cell and per-template record are fetched while the current one is being counted
+  int c_next = 0;
+  if (lane == 0) c_next = atomicAdd(p.queue, 1);
+  c_next = __shfl_sync(0xffffffffu, c_next, 0);
+  uint2 e_next = make_uint2(0u, 0u);
+  int4 fi_next = make_int4(0, 0, 0, 0);
+  if (c_next < total) {
+    e_next = __ldcg(p.cand + c_next);
+    fi_next = __ldg(p.finfo + e_next.x);
+  }
+  for (;;) {
+    const int c = c_next;
+    if (c >= total) break;
+    const uint2 e = e_next;
+    const int4 fi = fi_next;
+    if (lane == 0) c_next = atomicAdd(p.queue, 1);
+    c_next = __shfl_sync(0xffffffffu, c_next, 0);
+    if (c_next < total) {
+      e_next = __ldcg(p.cand + c_next);
+      fi_next = __ldg(p.finfo + e_next.x);
+    }
+    const int j = (int)e.y;
+    bool pass = true;
+    if (fi.w & 2) {
+      const int nf = fi.y;
+      const int need = (int)((unsigned)fi.w >> 8);
+      if (need > nf) {  // nothing can be kept (LL.cpp:1935-1937 would drop whatever the patch holds)
+        if (lane == 0) dropped_feats += (unsigned)nf;
+        pass = false;
+      } else if (need > 0) {
+        // patch origin of the candidate at the filtered level (LL.cpp:1871-1880, 1380-1381)
+        int x = (j % p.low.Wd) * p.low.T + p.low.off;
+        int y = (j / p.low.Wd) * p.low.T + p.low.off;
+        x = x * 2 + 1;
+        y = y * 2 + 1;
+        x = max(x, border); y = max(y, border);
+        x = min(x, p.ref.cols - (fi.z & 0xFFFF) - border);
+        y = min(y, p.ref.rows - (int)((unsigned)fi.z >> 16) - border);
+        const char* __restrict__ col = reinterpret_cast<const char*>(p.rp + (x / T - 8 + gl));  // this lane's first column
+        const int cy = y / T - 8;
+        const uint32_t* __restrict__ fd = p.rdesc + fi.x;
+        const int nfp = (nf + 31) & ~31;  // descriptors are padded with zero-plane entries
+        // check points: multiples of 32 features nearest to 1/2 and 3/4 of the template
+        const int chk1 = ((nf / 2 + 31) & ~31), chk2 = ((nf * 3 / 4 + 31) & ~31);
+        uint32_t ch[LM_FILTER_BITS];
+#pragma unroll
+        for (int b = 0; b < LM_FILTER_BITS; ++b) ch[b] = 0u;
+        bool lane_alive = true, dead = false;
+        uint32_t d_next = __ldg(fd + lane);
+        for (int i = 0; i < nfp; i += 32) {
+          // lane L decodes feature i + L: plane BYTE offset (incl. the row block of this candidate) : 27 | shift : 5
+          const uint32_t d = d_next;
+          if (i + 32 < nfp) d_next = __ldg(fd + i + 32 + lane);  // one step ahead
+          const int py0 = cy + (int)(d >> 23);
+          const uint32_t v = (((d & 0x7FFFFFu) + (uint32_t)((py0 >> 4) * Wd)) << 7) | ((uint32_t)py0 & 15u);
+          uint32_t xh[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t vu = __shfl_sync(0xffffffffu, v, u, 8);  // lane u of this lane's group
+            const uint32_t* __restrict__ ptr = lm_ptr_add(col, vu >> 5);
+            uint32_t w0 = 0u, w1 = 0u;
+            if (lane_alive) {
+              w0 = __ldg(ptr);
+              w1 = __ldg(ptr + 8);
+            }
+            // funnel shift = shift by the low 5 bits of vu (the row offset inside the word)
+            xh[u] = __byte_perm(__funnelshift_r(w0, 0u, vu), __funnelshift_r(w1, 0u, vu), 0x5410);
+          }
+          if (lane_alive) words_read += 16;
+          vc_add8n<LM_FILTER_BITS>(ch, xh);
+          const int done = i + 32;
+          if ((done == chk1 || done == chk2) && done < nf) {
+            vc_allreduce_groups(ch);  // every group now holds the totals of its 32 cells
+            const uint32_t alive_cells = vc_ge(ch, need - (nf - done));
+            lane_alive = alive_cells != 0u;
+            if (!__any_sync(0xffffffffu, lane_alive)) { dead = true; break; }
+            if (grp) {  // the totals live on in group 0; the others start their partial counts again
+#pragma unroll
+              for (int b = 0; b < LM_FILTER_BITS; ++b) ch[b] = 0u;
+            }
+          }
+        }
+        if (!dead) {
+          vc_allreduce_groups(ch);
+          dead = !__any_sync(0xffffffffu, vc_ge(ch, need) != 0u);
+        }
+        if (dead) {
+          if (lane == 0) dropped_feats += (unsigned)nf;  // the reference's work for it (algorithmic bytes / 256)
+          pass = false;
+        }
+      }
+    }
+    if (pass && lane == 0) {
+      if (p.surv2 && !(fi.w & 2)) p.surv2[atomicAdd(p.queue + 2, 1)] = (uint32_t)c;  // byte-wise refinement (k_refine)
+      else p.surv[atomicAdd(p.queue + 1, 1)] = (uint32_t)c;
+    }
+  }
+  words_read = __reduce_add_sync(0xffffffffu, words_read);
+  if (lane == 0 && (words_read | dropped_feats)) {
+    atomicAdd(p.counters + 4, (unsigned long long)dropped_feats);
+    atomicAdd(p.counters + 5, (unsigned long long)words_read);
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 // K3: local refinement, one warp per coarse candidate, all upper pyramid levels
 // --------------------------------------------------------------------------------------------
@@ -1106,6 +1388,21 @@ static __device__ __noinline__ void peer_publish(const PeerExchange* px, int seq
   }
 }
 
+// kept record -> result block (unordered append; (work, seq) restores the reference's pre-sort order on the host) and, in
+// multi-GPU mode, the same slot of this rank's block in every peer's buffer
+__device__ __forceinline__ void append_record(lm_result_header* hdr, int32_t capacity, const PeerExchange* px, int32_t px_seq,
+                                              int x, int y, float sim, int work, int seq) {
+  const int slot = atomicAdd(&hdr->count, 1);
+  if (slot < capacity) {
+    lm_record r;
+    r.x = (int16_t)x; r.y = (int16_t)y; r.similarity = sim;
+    r.work = work;
+    r.seq = seq;
+    reinterpret_cast<lm_record*>(hdr + 1)[slot] = r;
+    if (px) peer_store_record(px, px_seq, slot, *reinterpret_cast<const int4*>(&r));
+  }
+}
+
 struct RefineParams {
   const PeerExchange* px;  // device-resident descriptor of the fused multi-GPU exchange, or null
   int32_t px_seq;          // this frame's sequence number
@@ -1118,8 +1415,10 @@ struct RefineParams {
   const uint2* cand;     // ordered candidate list (k_refine_prep)
   int cand_cap;
   const uint16_t* raw;   // [n_work][plane_low] coarse raw scores (read when there is no level to refine)
-  const uint32_t* surv;  // survivors of k_refine_filter, or null: every candidate
-  const int* queue;      // [1] number of survivors
+  const uint32_t* surv;  // work items: a list of candidate indices written by k_refine_filter, or null: every candidate
+  const int* queue;      // queue[surv_slot] = length of that list
+  int surv_slot;
+  int publish;           // multi-GPU: this is the last kernel of the frame that appends records
   int n_work, L, S, M;
   int work_begin, work_stride;  // entry w of this shard is element work_begin + w * work_stride of the selected sequence
   float threshold;
@@ -1195,12 +1494,11 @@ __global__ void __launch_bounds__(256, LM_REFINE_MIN_CTAS) k_refine(RefineParams
   const LevelDev low = p.lv[p.L - 1];
   const int row = lane >> 1, half = lane & 1;
   unsigned feats_done = 0, rows_read = 0;  // per warp: a few candidates x (features x 16 rows)
-  lm_record* __restrict__ out = reinterpret_cast<lm_record*>(p.hdr + 1);
   if (p.bp_clear)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.bp_words; i += gridDim.x * blockDim.x) p.bp_clear[i] = 0u;
 
   // work items: the survivors of k_refine_filter (unordered candidate indices), or every candidate
-  const int n_items = p.surv ? min(__ldcg(p.queue + 1), total) : total;
+  const int n_items = p.surv ? min(__ldcg(p.queue + p.surv_slot), total) : total;
   for (int base = blockIdx.x * per_cta; base < n_items; base += gridDim.x * per_cta) {
     const int it = base + (kSplit ? (warp >> 2) : warp);
     const bool valid = it < n_items;
@@ -1374,24 +1672,229 @@ __global__ void __launch_bounds__(256, LM_REFINE_MIN_CTAS) k_refine(RefineParams
         kept = !pruned && !(sim < p.threshold);  // remove_if(similarity < threshold), LL.cpp:1935-1937
       }
     }
-    if (lane == 0 && kept && q == 0) {
-      // unordered append; (work, seq) restores the reference's pre-sort order on the host
-      const int slot = atomicAdd(&p.hdr->count, 1);
-      if (slot < p.capacity) {
-        lm_record r;
-        r.x = (int16_t)x; r.y = (int16_t)y; r.similarity = sim;
-        r.work = p.work_begin + w * p.work_stride;
-        r.seq = c;
-        out[slot] = r;
-        if (p.px) peer_store_record(p.px, p.px_seq, slot, *reinterpret_cast<const int4*>(&r));
-      }
-    }
+    if (lane == 0 && kept && q == 0)
+      append_record(p.hdr, p.capacity, p.px, p.px_seq, x, y, sim, p.work_begin + w * p.work_stride, c);
   }
   if (lane == 0 && (feats_done | rows_read)) {
     atomicAdd(p.counters + 0, (unsigned long long)feats_done);
     atomicAdd(p.counters + 1, (unsigned long long)rows_read);
   }
-  if (p.px) {
+  if (p.px && p.publish) {
+    __syncthreads();
+    if (threadIdx.x == 0) peer_publish(p.px, p.px_seq, p.hdr);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// k_refine_bits: the exact refinement of the filter's survivors, bit-sliced (two pyramid levels, i.e. the refined level
+// is level 0: the reference's default; deeper pyramids and the templates the filter does not take go to k_refine).
+//
+// similarityLocal's response is 4*H + N with H = the feature's label bit in the spread mask and N = (either neighbouring
+// label bit) & ~H (lm_response), so the exact 16x16 sums are raw = 4*CH + CN.  Same warp layout as k_refine_filter_w
+// (four 8-lane groups deal the features of the candidate between them, lane k of a group holds patch columns k and k + 8),
+// but three H-plane windows per feature (labels o - 1, o, o + 1) and two vertical counters.  The partial counters meet
+// once, at the end; the score 4*CH + CN, the best cell (max raw, lowest cell index = first maximum in row-major order,
+// LL.cpp:1910-1927) and the keep test (LL.cpp:1935-1937) are evaluated bit-sliced.  The byte linear memories are never
+// touched.
+// --------------------------------------------------------------------------------------------
+struct RefineBitsParams {
+  const uint32_t* rp;      // H-planes of level 0 (k_refine_prep), zero tail behind
+  int Wd;
+  int label_stride;        // words between the planes of consecutive labels: T*T * nyb * Wd
+  const uint32_t* rdesc;   // as FilterParams (padded to multiples of 32 per template)
+  const uint8_t* rlab;     // per descriptor: the feature's label 0..7, 8 = padding
+  const int4* finfo;
+  LevelDev low, ref;
+  const uint2* cand;
+  const int32_t* off;
+  int n_work, cand_cap;
+  const uint32_t* surv;
+  const int* queue;        // [1] survivors
+  float threshold;
+  int work_begin, work_stride;
+  lm_result_header* hdr;
+  int32_t capacity;
+  const PeerExchange* px;
+  int32_t px_seq;
+  int publish;
+  unsigned long long* counters;  // [0] features x candidates refined here, [5] plane words read
+  uint32_t* bp_clear;
+  uint32_t bp_words;
+};
+
+// bit-sliced add of two vertical counters
+__device__ __forceinline__ void vc_add(uint32_t (&c)[LM_FILTER_BITS], const uint32_t (&o)[LM_FILTER_BITS]) {
+  uint32_t carry = 0u;
+#pragma unroll
+  for (int b = 0; b < LM_FILTER_BITS; ++b) {
+    const uint32_t a = c[b], x = o[b];
+    c[b] = a ^ x ^ carry;
+    carry = (a & x) | (carry & (a ^ x));
+  }
+}
+
+// Four warps share a survivor (a candidate is a chain of nf / 32 dependent steps, and the survivors are too few to hide
+// it with other warps): warp q of the quad takes the 32-feature steps q, q + 4, ..., the partial counters meet in shared
+// memory and warp 0 of the quad finishes the candidate.
+__global__ void __launch_bounds__(256, 3) k_refine_bits(RefineBitsParams p) {
+  lm_pdl_wait();
+  __shared__ uint32_t s_part[8][2 * LM_FILTER_BITS][32];
+  const int lane = threadIdx.x & 31, gl = lane & 7, warp = threadIdx.x >> 5;
+  const int quad = warp >> 2, q = warp & 3;
+  const int total = min(p.off[p.n_work], p.cand_cap);
+  const int n_items = min(__ldcg(p.queue + 1), total);
+  const int T = p.ref.T, border = 8 * T;
+  const int Wd = p.Wd;
+  unsigned feats_done = 0, words_read = 0;
+  if (p.bp_clear)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.bp_words; i += gridDim.x * blockDim.x) p.bp_clear[i] = 0u;
+
+  for (int base = blockIdx.x * 2; base < n_items; base += gridDim.x * 2) {
+    const int it = base + quad;
+    const bool valid = it < n_items;
+    int c = 0, w = 0, x = 0, y = 0, nf = 0;
+    uint32_t ch[LM_FILTER_BITS], cn[LM_FILTER_BITS];
+#pragma unroll
+    for (int b = 0; b < LM_FILTER_BITS; ++b) ch[b] = cn[b] = 0u;
+    if (valid) {
+      c = (int)__ldcg(p.surv + it);
+      const uint2 e = __ldcg(p.cand + c);
+      w = (int)e.x;
+      const int j = (int)e.y;
+      const int4 fi = __ldg(p.finfo + w);
+      nf = fi.y;
+      x = (j % p.low.Wd) * p.low.T + p.low.off;
+      y = (j / p.low.Wd) * p.low.T + p.low.off;
+      x = x * 2 + 1;
+      y = y * 2 + 1;
+      x = max(x, border); y = max(y, border);  // LL.cpp:1875-1880 (max first, then min)
+      x = min(x, p.ref.cols - (fi.z & 0xFFFF) - border);
+      y = min(y, p.ref.rows - (int)((unsigned)fi.z >> 16) - border);
+      const char* __restrict__ col = reinterpret_cast<const char*>(p.rp + (x / T - 8 + gl));
+      const int cy = y / T - 8;
+      const uint32_t* __restrict__ fd = p.rdesc + fi.x;
+      const uint8_t* __restrict__ fl = p.rlab + fi.x;
+      const int nfp = (nf + 31) & ~31;
+      if (q == 0) feats_done += (unsigned)nf;
+
+      for (int i = q * 32; i < nfp; i += 128) {
+        // lane L decodes feature i + L: word offsets of the three label planes (row block of this candidate included)
+        // : 27 | row shift : 5
+        const uint32_t d = __ldg(fd + i + lane);
+        const int o = (int)__ldg(fl + i + lane);
+        const int py0 = cy + (int)(d >> 23);
+        const uint32_t idx = (d & 0x7FFFFFu) + (uint32_t)((py0 >> 4) * Wd);
+        const uint32_t sft = (uint32_t)py0 & 15u;
+        const int dm = o >= 8 ? 0 : (o == 0 ? 7 * p.label_stride : -p.label_stride);
+        const int dp = o >= 7 ? (o == 7 ? -7 * p.label_stride : 0) : p.label_stride;
+        const uint32_t v0 = (idx << 7) | sft;  // byte offset : 27 | row shift : 5
+        const uint32_t vm = ((uint32_t)((int)idx + dm) << 7) | sft;
+        const uint32_t vp = ((uint32_t)((int)idx + dp) << 7) | sft;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t xh[4], xn[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int src = half * 4 + u;  // lane `src` of this lane's group
+            const uint32_t a0 = __shfl_sync(0xffffffffu, v0, src, 8);
+            const uint32_t am = __shfl_sync(0xffffffffu, vm, src, 8);
+            const uint32_t ap = __shfl_sync(0xffffffffu, vp, src, 8);
+            const uint32_t* __restrict__ p0 = lm_ptr_add(col, a0 >> 5);
+            const uint32_t* __restrict__ pm = lm_ptr_add(col, am >> 5);
+            const uint32_t* __restrict__ pp = lm_ptr_add(col, ap >> 5);
+            const uint32_t h = __byte_perm(__funnelshift_r(__ldg(p0), 0u, a0), __funnelshift_r(__ldg(p0 + 8), 0u, a0), 0x5410);
+            const uint32_t a = __byte_perm(__funnelshift_r(__ldg(pm), 0u, a0), __funnelshift_r(__ldg(pm + 8), 0u, a0), 0x5410);
+            const uint32_t b = __byte_perm(__funnelshift_r(__ldg(pp), 0u, a0), __funnelshift_r(__ldg(pp + 8), 0u, a0), 0x5410);
+            xh[u] = h;
+            xn[u] = (a | b) & ~h;
+          }
+          // four 1-bit planes into each vertical counter
+          uint32_t t1a, t1b, t2;
+          CSA(ch[0], t1a, ch[0], xh[0], xh[1]);
+          CSA(ch[0], t1b, ch[0], xh[2], xh[3]);
+          CSA(ch[1], t2, ch[1], t1a, t1b);
+#pragma unroll
+          for (int b = 2; b < LM_FILTER_BITS; ++b) { const uint32_t k = ch[b] & t2; ch[b] ^= t2; t2 = k; }
+          CSA(cn[0], t1a, cn[0], xn[0], xn[1]);
+          CSA(cn[0], t1b, cn[0], xn[2], xn[3]);
+          CSA(cn[1], t2, cn[1], t1a, t1b);
+#pragma unroll
+          for (int b = 2; b < LM_FILTER_BITS; ++b) { const uint32_t k = cn[b] & t2; cn[b] ^= t2; t2 = k; }
+        }
+        words_read += 48;
+      }
+    }
+    // the quad's partial counters meet
+    if (q != 0) {
+#pragma unroll
+      for (int b = 0; b < LM_FILTER_BITS; ++b) {
+        s_part[warp][b][lane] = ch[b];
+        s_part[warp][LM_FILTER_BITS + b][lane] = cn[b];
+      }
+    }
+    __syncthreads();
+    if (q == 0 && valid) {
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        uint32_t oh[LM_FILTER_BITS], on[LM_FILTER_BITS];
+#pragma unroll
+        for (int b = 0; b < LM_FILTER_BITS; ++b) {
+          oh[b] = s_part[warp + k][b][lane];
+          on[b] = s_part[warp + k][LM_FILTER_BITS + b][lane];
+        }
+        vc_add(ch, oh);
+        vc_add(cn, on);
+      }
+      vc_allreduce_groups(ch);
+      vc_allreduce_groups(cn);
+      // raw = 4*CH + CN, 11 bits (4 * 511 < 2048)
+      uint32_t sc[11];
+      sc[0] = cn[0];
+      sc[1] = cn[1];
+      uint32_t carry = 0u;
+#pragma unroll
+      for (int b = 2; b < 11; ++b) {
+        const uint32_t a = (b < LM_FILTER_BITS) ? cn[b] : 0u;
+        const uint32_t h = ch[b - 2];
+        sc[b] = a ^ h ^ carry;
+        carry = (a & h) | (carry & (a ^ h));
+      }
+      // best raw score: highest bit first, keep the cells that still tie for the maximum
+      uint32_t cells = 0xffffffffu;
+      int best_raw = 0;
+#pragma unroll
+      for (int b = 10; b >= 0; --b) {
+        const uint32_t t = cells & sc[b];
+        if (__any_sync(0xffffffffu, t != 0u)) {
+          cells = t;
+          best_raw |= 1 << b;
+        }
+      }
+      // first maximum in row-major order: lowest row, then lowest column (bits 0..15 = rows of column gl, 16..31 = of
+      // gl + 8)
+      int cell = 0x7fffffff;
+      if (cells & 0xFFFFu) cell = (__ffs(cells & 0xFFFFu) - 1) * 16 + gl;
+      if (cells >> 16) cell = min(cell, (__ffs(cells >> 16) - 1) * 16 + gl + 8);
+      cell = __reduce_min_sync(0xffffffffu, cell);
+      int br = -1, bc = -1;
+      if (best_raw > 0) {
+        br = cell >> 4;
+        bc = cell & 15;
+      }
+      const float sim = lm_score(best_raw, nf);
+      x = (x / T - 8 + bc) * T + p.ref.off;  // LL.cpp:1930-1931
+      y = (y / T - 8 + br) * T + p.ref.off;
+      if (lane == 0 && !(sim < p.threshold))  // remove_if(similarity < threshold), LL.cpp:1935-1937
+        append_record(p.hdr, p.capacity, p.px, p.px_seq, x, y, sim, p.work_begin + w * p.work_stride, c);
+    }
+    __syncthreads();  // before the next candidate's partials overwrite these
+  }
+  words_read = __reduce_add_sync(0xffffffffu, words_read);
+  if (lane == 0 && (feats_done | words_read)) {
+    atomicAdd(p.counters + 0, (unsigned long long)feats_done);
+    atomicAdd(p.counters + 5, (unsigned long long)words_read);
+  }
+  if (p.px && p.publish) {
     __syncthreads();
     if (threadIdx.x == 0) peer_publish(p.px, p.px_seq, p.hdr);
   }

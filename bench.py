@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: record exchange fused into the refinement kernel (peer stores over NVLink) or one "
                          "NCCL all-gather of result blocks per frame (the baseline)")
+    ap.add_argument("--shards", default="interleaved", choices=["interleaved", "contiguous"],
+                    help="N>1: template shard layout (interleaved: rank r takes templates r, r+N, ...: even candidate load)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run result check against the oracle")
     ap.add_argument("--seed", type=int, default=1234)
     return ap.parse_args()
 
@@ -186,12 +189,26 @@ def run_reference(args):
     emit(json.dumps(out))
 
 
+def oracle_expected(args, packed, quantized, world):
+    """The reference's result for one frame of the workload (CPU oracle, test infrastructure: the checker only)."""
+    from oracle import oracle
+    threads = max(1, (os.cpu_count() or 1) // max(world, 1))
+    return oracle.match(quantized, T_PYR, packed, args.threshold, n_threads=min(threads, 64))
+
+
+def same_matches(got, want):
+    if len(got) != len(want):
+        return False
+    return (all(np.array_equal(got[k], want[k]) for k in ("x", "y", "template_id", "similarity"))
+            and np.array_equal(got["class_index"], want["class_idx"]))
+
+
 def workload_config(args, n):
     return {"workload": "obj_01-like synthetic bank, %d templates (89 views x 35 variants), %d features/modality at L0, "
                         "T=[4,8], %dx%d quantized RGB-D frames, threshold %g, 8 planted templates per frame"
                         % (args.templates, args.features, args.width, args.height, args.threshold),
             "templates": args.templates, "frame": [args.width, args.height], "threshold": args.threshold,
-            "parallelism": "template-shard x%d" % n, "lanes": args.lanes,
+            "parallelism": "template-shard x%d (%s)" % (n, args.shards), "lanes": args.lanes,
             "exchange": "none" if n == 1 else ("fused into k_refine (peer stores over NVLink + collector kernel)"
                                                if args.exchange == "fused" else "nccl all-gather of result blocks"),
             "l2": "ring of %d distinct frames (%.0f MB of label images > 126 MB L2); bank and linear memories are "
@@ -232,10 +249,11 @@ def main():
     bank, frames = make_workload(args, args.ring)
     packed = bank.pack(bank.class_ids(), 4)
     nats = []
+    layout = lib.SHARD_INTERLEAVED if args.shards == "interleaved" else lib.SHARD_CONTIGUOUS
     for _ in range(max(1, args.lanes)):
         n_ = lib.NativeDetector(T_PYR, device=local)
         n_.load_bank(packed, 4)
-        n_.select(None, rank, world)
+        n_.select(None, rank, world, layout)
         nats.append(n_)
     nat = nats[0]
 
@@ -249,6 +267,9 @@ def main():
     stream = torch.cuda.ExternalStream(nat.stream(), device=local)
     lane_streams = [torch.cuda.ExternalStream(n_.stream(), device=local) for n_ in nats]
 
+    for n_ in nats:  # everything lazy (feature addresses for this frame size, work lists, buffers) now: no rank's
+        n_.bind_quantized_device(ring[0][1], rows, cols)  # first frame lags the others' behind the barrier below
+        n_.prepare()
     cap = 16384
     blk_bytes = 16 + 16 * cap
     fused = world > 1 and args.exchange == "fused"
@@ -322,6 +343,42 @@ def main():
         launches = int(lt.item())
     fps = args.steps / (ms / 1e3)
 
+    # ---- result check: the frames at both ends of the timed region, through every lane (same calls as the timed loop:
+    # bind -> enqueue -> complete), against the oracle's list.  A mismatch fails the run.
+    parity = {"checked": False, "ok": None, "frames": 0}
+    if not args.no_parity:
+        ok_all = True
+        check_ids = sorted({(args.warmup) % len(ring), (args.warmup + args.steps - 1) % len(ring)})
+        for fi in check_ids:
+            want = oracle_expected(args, packed, frames[fi], world)
+            for n_ in (nats if (fused or world == 1) else nats[:1]):
+                n_.bind_quantized_device(ring[fi][1], rows, cols)
+                n_.enqueue(args.threshold)
+            if world > 1 and not fused:
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(gathered, res)
+                    host = gathered.to("cpu", non_blocking=False)
+            for k_, n_ in enumerate(nats if (fused or world == 1) else nats[:1]):
+                n_.complete()
+                if world > 1 and not fused:
+                    blocks = host.numpy().reshape(world, blk_bytes)
+                    rec = np.concatenate([blocks[r, 16:16 + 16 * int(blocks[r, :4].view(np.int32)[0])].view(lib.RECORD_DTYPE)
+                                          for r in range(world)])
+                else:
+                    rec = n_.fetch_records()
+                got = n_.finish(rec)
+                good = same_matches(got, want)
+                if not good:
+                    sys.stderr.write("PARITY MISMATCH rank %d lane %d frame %d: got %d matches, oracle %d\n" % (rank, k_, fi, len(got), len(want)))
+                ok_all = ok_all and good
+                parity["frames"] += 1
+        parity["checked"], parity["ok"] = True, bool(ok_all)
+        if world > 1:
+            t = torch.tensor([1 if ok_all else 0], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            parity["ok"] = bool(int(t.item()))
+    barrier()
+
     # ---- per-kernel durations over K more steps (CUDA events on the launching stream) ------------
     all_lanes, nats = nats, nats[:1]     # one lane: stage durations without overlap
     nat.set_timing(min(args.steps, 256))
@@ -373,6 +430,22 @@ def main():
         out = e2e_step(i)
     barrier()
     n_e2e = min(args.steps, 100)
+    if not args.no_parity:
+        # first and last frame of the e2e passes, through the same blocking call
+        ok_e2e = True
+        for fi in sorted({0, (n_e2e - 1) % len(host_frames)}):
+            got = e2e_step(fi)
+            good = same_matches(got, oracle_expected(args, packed, frames[fi], world))
+            if not good:
+                sys.stderr.write("PARITY MISMATCH (e2e) rank %d frame %d\n" % (rank, fi))
+            ok_e2e = ok_e2e and good
+            parity["frames"] += 1
+        if world > 1:
+            t = torch.tensor([1 if ok_e2e else 0], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok_e2e = bool(int(t.item()))
+        parity["ok"] = bool(parity["ok"] and ok_e2e)
+        barrier()
     # the blocking call is host-latency bound (sync wake-ups, ctypes): 3 passes of n_e2e steps, the MEDIAN pass is
     # reported so that one scheduler hiccup on a shared host does not decide the number
     passes = []
@@ -446,6 +519,8 @@ def main():
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
+        if parity["checked"] and not parity["ok"]:
+            raise SystemExit(1)
         return
 
     peaks = {}
@@ -483,7 +558,13 @@ def main():
             "k_scan_counts": {"us": stage["offsets"],
                               "note": "the offset scan runs in the last CTA of the coarse scan (inside k_coarse_scan.us) "
                                       "unless the bank needs k_coarse_bytes; this is the gap between the two events"},
-            "k_refine": {"us": refine_us, "alg_bytes": counters["refine_bytes"], "gbs": refine_gbs, "frac": refine_gbs / hbm},
+            "k_refine": {"us": refine_us, "alg_bytes": counters["refine_bytes"], "gbs": refine_gbs, "frac": refine_gbs / hbm,
+                         "parts_us": {"k_refine_prep (candidate list + H-planes)": stage["refine_prep"],
+                                      "k_refine_filter (bit-sliced upper bound)": stage["refine_filter"],
+                                      "k_refine<split> (exact, survivors)": stage["refine_exact"]},
+                         "filter_dropped_alg_bytes": counters.get("filter_dropped_bytes"),
+                         "filter_plane_bytes_read": counters.get("filter_bytes_read"),
+                         "exact_lm_bytes_read": counters.get("refine_bytes_read")},
             "stages_total_us": stage["total"],
         },
     }
@@ -496,6 +577,10 @@ def main():
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // max(n_e2e, 1),
                 "steps": n_e2e, "passes_s": passes, "concurrent_callers": conc, "match_top3": top3, "api": "lm_match_quantized (C-ABI), pinned host label images -> matches"},
         "gpu_launches": launches,
+        "parity_checked": bool(parity["checked"] and parity["ok"]),
+        "parity": dict(parity, against="CPU oracle (oracle/lm_oracle.cpp) on the frames at both ends of the timed region, every lane, "
+                                       "and on the first / last frame of the e2e passes; match lists compared field by field, float ==",
+                       ),
         "roofline": roofline,
         "counters": counters, "counters_note": "per-frame averages over the frames of the stage-timing pass",
     }
@@ -567,6 +652,8 @@ def main():
     emit(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+    if parity["checked"] and not parity["ok"]:
+        raise SystemExit("bench.py: results differ from the oracle (see stderr)")
 
 
 if __name__ == "__main__":
