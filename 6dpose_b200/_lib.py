@@ -250,6 +250,15 @@ class NativeDetector:
         c = (ctypes.c_int * len(cols))(*[int(x) for x in cols])
         check(self._L.lm_bind_quantized_device(self._h, p, r, c))
 
+    @staticmethod
+    def bind_args(ptrs, rows, cols):
+        """The ctypes arrays of bind_quantized_device, built once for a frame that is bound many times."""
+        return ((ctypes.c_void_p * len(ptrs))(*[int(x) for x in ptrs]), (ctypes.c_int * len(rows))(*[int(x) for x in rows]),
+                (ctypes.c_int * len(cols))(*[int(x) for x in cols]))
+
+    def bind_quantized_device_args(self, args):
+        check(self._L.lm_bind_quantized_device(self._h, args[0], args[1], args[2]))
+
     def run(self, threshold):
         check(self._L.lm_run(self._h, ctypes.c_float(threshold)))
 

@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--templates", type=int, default=3115)
+    ap.add_argument("--templates", type=int, default=3115, help="templates per object")
+    ap.add_argument("--objects", type=int, default=1, help="objects (classes) in the bank: config 4 = 6 x 3115")
+    ap.add_argument("--no-extras", action="store_true", help="N=1: skip the real-data arm, threshold sweep, front-end, ICP blocks")
     ap.add_argument("--features", type=int, default=150)
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--height", type=int, default=480)
@@ -49,9 +51,10 @@ def parse():
     ap.add_argument("--ring", type=int, default=176, help="distinct frames cycled through (176 x 768 KB > 126 MB L2)")
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the same workload timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=3,
+    ap.add_argument("--lanes", type=int, default=0,
                     help="frames in flight per GPU for `value`: one handle (stream + buffers) per lane, frames "
-                         "alternate between lanes so that the small kernels of one frame fill the tail of another")
+                         "alternate between lanes so that the small kernels of one frame fill the tail of another "
+                         "(default: 3 on one GPU, 6 with the bank sharded: a shard's kernels are short chains)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: record exchange fused into the refinement kernel (peer stores over NVLink) or one "
                          "NCCL all-gather of result blocks per frame (the baseline)")
@@ -67,7 +70,8 @@ T_PYR = [4, 8]
 
 def make_workload(args, n_frames):
     synth = importlib.import_module("6dpose_b200.synth")
-    bank = synth.synth_bank(args.templates, num_features=args.features, levels=2, seed=args.seed, variants=35)
+    cids = tuple("%02d_template" % (k + 1) for k in range(max(args.objects, 1)))
+    bank = synth.synth_bank(args.templates, num_features=args.features, levels=2, seed=args.seed, variants=35, class_ids=cids)
     frames = []
     for i in range(n_frames):
         q, _ = synth.synth_frame(args.width, args.height, levels=2, seed=1000 + i, bank=bank, plant=8, T=T_PYR)
@@ -88,7 +92,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -203,11 +207,152 @@ def same_matches(got, want):
             and np.array_equal(got["class_index"], want["class_idx"]))
 
 
+def _device_loop_fps(torch, nat, stream, threshold, steps):
+    """frames/s of `steps` enqueues of the frame currently bound to `nat`, CUDA events on its stream."""
+    for _ in range(5):
+        nat.enqueue(threshold)
+    nat.complete()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        nat.enqueue(threshold)
+    e1.record(stream)
+    nat.complete()
+    return steps / (e0.elapsed_time(e1) / 1e3)
+
+
+def real_data_arm(lib, torch, local):
+    """The reference's own fixture frame (linemodLevelup/test/case1/0000_*) against its full allScales bank (2989
+    templates, Detector() = 63 features, T = {5, 8}; test.cpp:174-181), thresholds 80 (the reference's invocation) and 75
+    (61 912 coarse candidates): results checked against the lists the compiled reference produced
+    (tests/golden/expected_allScales_full.npz).  One frame repeated, i.e. L2-resident inputs: a candidate-load check of
+    the kernels on real data, not a second headline."""
+    g = os.path.join(ROOT, "tests", "golden")
+    b = np.load(os.path.join(g, "bank_allScales_full.npz"))
+    packed = dict(class_begin=b["class_begin"], tmeta=b["tmeta"].astype(np.int32), feats=b["feats"].astype(np.int32))
+    T = b["T"].tolist()
+    fr = np.load(os.path.join(g, "frames_case1.npz"))
+    q = [[np.ascontiguousarray(fr["full_l%d_m%d" % (l, m)]) for m in range(2)] for l in range(2)]
+    exp = np.load(os.path.join(g, "expected_allScales_full.npz"))
+    nat = lib.NativeDetector(T, device=local)
+    nat.load_bank(packed, 4)
+    stream = torch.cuda.ExternalStream(nat.stream(), device=local)
+    ts = [torch.from_numpy(q[l][m]).cuda() for l in range(2) for m in range(2)]
+    rows, cols = [q[0][0].shape[0], q[1][0].shape[0]], [q[0][0].shape[1], q[1][0].shape[1]]
+    hq = [[torch.from_numpy(q[l][m]).pin_memory().numpy() for m in range(2)] for l in range(2)]
+    out = {"workload": "fixture frame 640x480 x allScales (2989 templates, 63 features/modality at L0, T=[5,8]); one frame "
+                       "repeated (inputs L2-resident), 1 frame in flight", "thresholds": {}}
+    for thr in (80.0, 75.0):
+        got = nat.match_quantized(hq, thr)
+        want = exp["full_%g" % thr]
+        ok = len(got) == len(want) and all(np.array_equal(got[k], want[k]) for k in ("x", "y", "template_id", "similarity"))
+        c = nat.counters()
+        nat.bind_quantized_device([t.data_ptr() for t in ts], rows, cols)
+        fps = _device_loop_fps(torch, nat, stream, thr, 100)
+        nat.set_timing(50)
+        for _ in range(50):
+            nat.enqueue(thr)
+        nat.complete()
+        st = nat.stage_times_us()
+        nat.set_timing(0)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            nat.match_quantized(hq, thr)
+        e2e = 50 / (time.perf_counter() - t0)
+        out["thresholds"]["%g" % thr] = {"matches": int(len(got)), "identical_to_compiled_reference": bool(ok),
+                                         "coarse_candidates": c["coarse_candidates"], "frames_per_s": fps,
+                                         "e2e_frames_per_s": e2e, "stage_us": st}
+    nat.close()
+    return out
+
+
+def threshold_sweep(lib, torch, local, args, packed, ring, rows, cols):
+    """Candidate-rate sweep on the synthetic workload: thresholds 75 and 90, one frame in flight."""
+    nat = lib.NativeDetector(T_PYR, device=local)
+    nat.load_bank(packed, 4)
+    stream = torch.cuda.ExternalStream(nat.stream(), device=local)
+    out = {}
+    for thr in (75.0, 90.0):
+        nat.bind_quantized_device(ring[0][1], rows, cols)
+        nat.enqueue(thr)
+        nat.complete()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 64
+        e0.record(stream)
+        for i in range(n):
+            nat.bind_quantized_device(ring[i % len(ring)][1], rows, cols)
+            nat.enqueue(thr)
+        e1.record(stream)
+        nat.complete()
+        c = nat.counters()
+        out["%g" % thr] = {"frames_per_s_1_lane": n / (e0.elapsed_time(e1) / 1e3), "coarse_candidates_last_frame": c["coarse_candidates"],
+                           "kept_last_frame": c["kept"]}
+    nat.close()
+    return out
+
+
+def pose_pipeline(lib, local):
+    """BASELINE.json config 3 as ONE figure: raw RGB-D frame -> match -> greedy NMS top-3 on the device -> poseRefine of the
+    three hypotheses (max 10 ICP iterations) in one batched call.  Inputs: the frame, bank and render of the recorded
+    driver run (tests/golden/driver_trace.npz, bank_allScales_full.npz).  Pose error against the ICP oracle with the same
+    iteration cap (PARITY UNPINNED: the reference's ICP arithmetic is Open3D's, see oracle/icp_oracle.py)."""
+    g = os.path.join(ROOT, "tests", "golden")
+    tr = np.load(os.path.join(g, "driver_trace.npz"))
+    b = np.load(os.path.join(g, "bank_allScales_full.npz"))
+    packed = dict(class_begin=b["class_begin"], tmeta=b["tmeta"].astype(np.int32), feats=b["feats"].astype(np.int32))
+    nat = lib.NativeDetector(tr["T"].tolist(), device=local)
+    nat.load_bank(packed, 4)
+    nat.set_boxes(np.full((int(packed["class_begin"][-1]), 2), 70, np.int32))  # the driver's info files: 70 x 70 boxes
+    icp = lib.NativeIcp(local)
+    rgb, depth, render = tr["rgb"], tr["depth"], tr["render"]
+    K, Km, R, t = tr["rf0_sceneK"], tr["rf0_modelK"], tr["rf0_modelR"], tr["rf0_modelT"].reshape(3)
+    thr = float(tr["threshold"])
+
+    def once(max_it=10):
+        nat.upload_images(rgb, depth)
+        nat.enqueue(thr)
+        nat.enqueue_post(0.5, 3)
+        top, nrec = nat.complete_post()
+        n = len(top)
+        if n == 0:
+            return top, None
+        xy = [[int(m["x"]), int(m["y"])] for m in top]
+        return top, icp.process_batch(depth, [render] * n, K, np.stack([Km] * n), np.stack([R] * n), np.stack([t] * n), xy, max_it)
+
+    for _ in range(3):
+        top, res = once()
+    n_it = 30
+    t0 = time.perf_counter()
+    for _ in range(n_it):
+        top, res = once()
+    dt = time.perf_counter() - t0
+    out = {"frames_per_s": n_it / dt, "ms_per_frame": dt / n_it * 1e3, "hypotheses": int(len(top)), "max_iterations": 10,
+           "top": [[int(m["x"]), int(m["y"]), int(m["template_id"]), float(m["similarity"])] for m in top],
+           "note": "lm_upload_images + lm_enqueue + lm_enqueue_post (NMS IoU 0.5, top 3) + lm_icp_process_batch; host buffers in, "
+                   "poses out; ICP parity unpinned (Open3D)"}
+    try:
+        from oracle import icp_oracle
+        errs = []
+        for i, m in enumerate(top):
+            o = icp_oracle.pose_refine(depth, render, K, Km, R, t, int(m["x"]), int(m["y"]), max_iter=10)
+            if o["R"] is None:
+                continue
+            errs.append(max(float(np.linalg.norm(res[0][i] - o["R"]) / np.linalg.norm(o["R"])),
+                            float(np.linalg.norm(res[1][i] - o["t"].reshape(3)) / np.linalg.norm(o["t"]))))
+        out["pose_rel_error_vs_icp_oracle_max"] = max(errs) if errs else None
+        out["fitness"] = [float(v) for v in res[2]]
+    except Exception as e:  # informative only
+        out["pose_rel_error_vs_icp_oracle_max"] = repr(e)
+    nat.close()
+    return out
+
+
 def workload_config(args, n):
-    return {"workload": "obj_01-like synthetic bank, %d templates (89 views x 35 variants), %d features/modality at L0, "
+    return {"workload": "obj_01-like synthetic bank, %d object(s) x %d templates (views x 35 variants), %d features/modality at L0, "
                         "T=[4,8], %dx%d quantized RGB-D frames, threshold %g, 8 planted templates per frame"
-                        % (args.templates, args.features, args.width, args.height, args.threshold),
-            "templates": args.templates, "frame": [args.width, args.height], "threshold": args.threshold,
+                        % (args.objects, args.templates, args.features, args.width, args.height, args.threshold),
+            "templates": args.templates * args.objects, "objects": args.objects, "frame": [args.width, args.height],
+            "threshold": args.threshold,
             "parallelism": "template-shard x%d (%s)" % (n, args.shards), "lanes": args.lanes,
             "exchange": "none" if n == 1 else ("fused into k_refine (peer stores over NVLink + collector kernel)"
                                                if args.exchange == "fused" else "nccl all-gather of result blocks"),
@@ -245,6 +390,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    if args.lanes <= 0:
+        args.lanes = 3 if world == 1 else 6
     lib = importlib.import_module("6dpose_b200._lib")
     bank, frames = make_workload(args, args.ring)
     packed = bank.pack(bank.class_ids(), 4)
@@ -288,10 +435,11 @@ def main():
         nat.set_result_buffer(res.data_ptr(), cap)
         gathered = torch.zeros(world * blk_bytes, dtype=torch.uint8, device="cuda")
 
+    bind_args = [lib.NativeDetector.bind_args(ptrs, rows, cols) for _, ptrs in ring]  # ctypes arrays built once
+
     def step(i):
-        ts, ptrs = ring[i % len(ring)]
         n_ = nats[i % len(nats)] if (fused or world == 1) else nat
-        n_.bind_quantized_device(ptrs, rows, cols)
+        n_.bind_quantized_device_args(bind_args[i % len(ring)])
         n_.enqueue(args.threshold)
         if world > 1 and not fused:
             with torch.cuda.stream(stream):
@@ -313,14 +461,14 @@ def main():
             ev.record(ls)
             stream.wait_event(ev)
 
+    sampler = ClockSampler(local)   # clocks / throttle reasons from the warm-up to the end of the timed region
+    sampler.start()
     for i in range(max(args.warmup, 3) * len(nats)):
         step(i)
     complete_all()
     barrier()
 
     # ---- timed region: K steps, device resident --------------------------------------------------
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = sum(n_.launch_count() for n_ in nats)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -584,7 +732,15 @@ def main():
         "roofline": roofline,
         "counters": counters, "counters_note": "per-frame averages over the frames of the stage-timing pass",
     }
-    if world == 1:
+    if world == 1 and not args.no_extras:
+        for name, fn in (("real_data", lambda: real_data_arm(lib, torch, local)),
+                         ("threshold_sweep", lambda: threshold_sweep(lib, torch, local, args, packed, ring, rows, cols)),
+                         ("pose_pipeline", lambda: pose_pipeline(lib, local))):
+            try:
+                out[name] = fn()
+            except Exception as e:  # informative blocks: never lose the headline line over them
+                out[name] = {"error": repr(e)}
+    if world == 1 and not args.no_extras:
         # quantization front-end (upstream of the metric): raw 640x480 RGB-D -> label pyramids, GPU kernels
         # (incl. the 1.5 MB H2D of the raw frame) vs the cv2 calls the reference makes; identical outputs
         synth = importlib.import_module("6dpose_b200.synth")
@@ -607,10 +763,12 @@ def main():
         for _ in range(20):
             mi = nat.match_images(rgb_p, dep_p, None, args.threshold)
         mi_ms = (time.perf_counter() - t0) / 20 * 1e3
-        out["frontend"] = {"gpu_ms_per_frame": gpu_ms, "cv2_ms_per_frame": cv2_ms, "match_images_ms_per_frame": mi_ms,
+        out["frontend"] = {"gpu_ms_per_frame": gpu_ms, "cv2_ms_per_frame": cv2_ms, "match_images_synth_rgbd_ms_per_frame": mi_ms,
                            "note": "lm_upload_images (H2D of raw RGB-D + 9 kernels + sync) vs 6dpose_b200/frontend.py (cv2); "
-                                   "match_images = Detector::match from raw images through the C-ABI (lm_match_images)"}
-    if world == 1:
+                                   "match_images_synth_rgbd = lm_match_images on a structured synthetic RGB-D image WITHOUT planted "
+                                   "templates (few candidates): a front-end figure, not comparable with e2e (see pose_pipeline / "
+                                   "real_data for whole-frame figures on the reference's fixture)"}
+    if world == 1 and not args.no_extras:
         # poseRefine (BASELINE.json config 2): the drivers refine the first three NMS survivors; here as one batched
         # call on the reference's own ICP fixture (tests/golden/icp_case1.npz = test/case1/pose/*), host buffers
         try:
