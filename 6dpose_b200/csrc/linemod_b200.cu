@@ -87,6 +87,7 @@ struct LevelHost {
   uint32_t mod_stride = 0;
   uint32_t* d_bp = nullptr;  // lowest level only: spread bit-planes [M][8][lbw]
   int lbw = 0, nwords = 0, rounds = 0;
+  int bp_zero = 0;   // words of zeros behind the bit-planes (where skipped / padding descriptors point)
 };
 
 struct lm_detector {
@@ -110,7 +111,10 @@ struct lm_detector {
   TSlot* d_tslot = nullptr;
   uint32_t* d_fbase = nullptr;
   uint32_t* d_fxy = nullptr;
-  uint2* d_fdesc = nullptr;          // lowest-level features, bit-plane addressing
+  uint4* d_fdesc4 = nullptr;         // lowest-level features for k_coarse_packed: byte offsets of the label's plane window and of
+                                     // its two neighbour labels' (x, y, z) + bit shift (w); per (template, modality) padded to
+                                     // a multiple of 8 with entries that point at the all-zero words behind the planes
+  int2* d_k2info = nullptr;          // [G][M]: first descriptor, padded count
   std::vector<uint8_t> bits_ok;      // per template: the bit-sliced coarse kernel may take it
   std::vector<uint8_t> safe;         // per template: refinement never skips a feature (LL.cpp:1394)
   uint8_t* d_safe = nullptr;
@@ -300,7 +304,7 @@ extern "C" void lm_destroy(lm_detector* d) {
   if (d->stream) cudaStreamSynchronize(d->stream);
   peer_release(d);
   for (int l = 0; l < LM_MAX_LEVELS; ++l) free_level(d->lv[l]);
-  cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_fdesc); cudaFree(d->d_work);
+  cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_fdesc4); cudaFree(d->d_k2info); cudaFree(d->d_work);
   cudaFree(d->d_items_bits); cudaFree(d->d_items_bytes); cudaFree(d->d_safe); cudaFree(d->d_galign);
   cudaFree(d->d_mask); cudaFree(d->d_raw); cudaFree(d->d_cnt); cudaFree(d->d_off);
   cudaFree(d->d_res_own); cudaFree(d->d_counters);
@@ -365,13 +369,12 @@ extern "C" int lm_load_bank(lm_detector* d, int n_classes, const int32_t* class_
   d->post_dirty = true;
   d->feats.assign(feats, feats + (size_t)n_feats * 3);
   d->feat_slot.swap(slot_of);
-  cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_fdesc);
-  d->d_tslot = nullptr; d->d_fbase = nullptr; d->d_fxy = nullptr; d->d_fdesc = nullptr;
+  cudaFree(d->d_tslot); cudaFree(d->d_fbase); cudaFree(d->d_fxy); cudaFree(d->d_fdesc4); cudaFree(d->d_k2info);
+  d->d_tslot = nullptr; d->d_fbase = nullptr; d->d_fxy = nullptr; d->d_fdesc4 = nullptr; d->d_k2info = nullptr;
   if (d->device >= 0 && G > 0) CU(cudaMalloc(&d->d_tslot, sizeof(TSlot) * (size_t)G * n_slots));
   if (d->device >= 0 && n_feats > 0) {
     CU(cudaMalloc(&d->d_fbase, sizeof(uint32_t) * (size_t)n_feats));
     CU(cudaMalloc(&d->d_fxy, sizeof(uint32_t) * (size_t)n_feats));
-    CU(cudaMalloc(&d->d_fdesc, sizeof(uint2) * (size_t)n_feats));
   }
   d->prepared = false;
   d->have_run = false;
@@ -471,7 +474,6 @@ static int prepare_bank(lm_detector* d) {
   if (same) return LM_OK;
   const size_t nf = d->feat_slot.size();
   std::vector<uint32_t> fbase(nf, 0), fxy(nf, 0);
-  std::vector<uint2> fdesc(nf, make_uint2(0u, LM_SKIP_BIT));
   const int low_level = d->L - 1;
   for (size_t i = 0; i < nf; ++i) {
     const int s = d->feat_slot[i];
@@ -486,14 +488,6 @@ static int prepare_bank(lm_detector* d) {
     uint32_t v = (uint32_t)x | ((uint32_t)y << 16);
     if (x >= lv.cols || y >= lv.rows) v |= LM_SKIP_BIT;  // LL.cpp:1330
     fxy[i] = v;
-    if (l == low_level && lv.d_bp) {
-      // flat bit address inside the label block: grid * plane + position (same order as the bytes)
-      const uint64_t inner = (uint64_t)((y % T) * T + (x % T)) * lv.plane + (uint64_t)(y / T) * lv.Wd + (x / T);
-      uint2 dsc;
-      dsc.x = (uint32_t)((uint64_t)(m * 8 + lab) * lv.lbw + (inner >> 5));
-      dsc.y = (uint32_t)(inner & 31) | ((uint32_t)lab << 8) | (v & LM_SKIP_BIT);
-      fdesc[i] = dsc;
-    }
   }
   d->h_tslot.resize((size_t)d->G * d->S);
   for (int g = 0; g < d->G; ++g)
@@ -523,6 +517,46 @@ static int prepare_bank(lm_detector* d) {
         same = same && t.z == t0.z;
       }
       d->bits_ok[g] = (total <= 255 && same) ? 1 : 0;
+    }
+  }
+  // k_coarse_packed descriptors: per lowest-level feature the byte offsets (inside the bit-plane buffer) of the window
+  // start of its label's plane and of the two neighbouring labels' planes, and the bit shift.  Features outside the
+  // image (LL.cpp:1330) and the padding to a multiple of 8 per (template, modality) point at the zero words behind the
+  // planes, so the kernel's loop has neither a skip branch nor a bounds check.
+  cudaFree(d->d_fdesc4); d->d_fdesc4 = nullptr;
+  cudaFree(d->d_k2info); d->d_k2info = nullptr;
+  {
+    const LevelHost& lv = d->lv[low_level];
+    if (lv.d_bp && d->G > 0) {
+      std::vector<uint4> f4;
+      std::vector<int2> k2((size_t)d->G * d->M);
+      const uint32_t zoff = (uint32_t)((size_t)d->M * 8 * lv.lbw) * 4u;  // byte offset of the zero words
+      const int T = lv.T;
+      for (int g = 0; g < d->G; ++g)
+        for (int m = 0; m < d->M; ++m) {
+          const int32_t* tm = &d->tmeta[((size_t)g * d->S + low_level * d->M + m) * 4];
+          k2[(size_t)g * d->M + m].x = (int)f4.size();
+          for (int k = 0; k < tm[3]; ++k) {
+            const size_t i = (size_t)tm[2] + k;
+            const int x = d->feats[3 * i], y = d->feats[3 * i + 1], lab = d->feats[3 * i + 2];
+            if (x >= lv.cols || y >= lv.rows) {
+              f4.push_back(make_uint4(zoff, zoff, zoff, 0u));
+              continue;
+            }
+            const uint64_t inner = (uint64_t)((y % T) * T + (x % T)) * lv.plane + (uint64_t)(y / T) * lv.Wd + (x / T);
+            const uint64_t wh = (uint64_t)(m * 8 + lab) * lv.lbw + (inner >> 5);
+            const uint64_t wm = (uint64_t)(m * 8 + ((lab + 7) & 7)) * lv.lbw + (inner >> 5);
+            const uint64_t wp = (uint64_t)(m * 8 + ((lab + 1) & 7)) * lv.lbw + (inner >> 5);
+            f4.push_back(make_uint4((uint32_t)(wh * 4), (uint32_t)(wm * 4), (uint32_t)(wp * 4), (uint32_t)(inner & 31)));
+          }
+          while ((f4.size() - (size_t)k2[(size_t)g * d->M + m].x) % 8) f4.push_back(make_uint4(zoff, zoff, zoff, 0u));
+          k2[(size_t)g * d->M + m].y = (int)(f4.size() - (size_t)k2[(size_t)g * d->M + m].x);
+        }
+      CU(cudaMalloc(&d->d_fdesc4, std::max<size_t>(f4.size(), 1) * sizeof(uint4)));
+      CU(cudaMalloc(&d->d_k2info, k2.size() * sizeof(int2)));
+      if (!f4.empty()) CU(cudaMemcpyAsync(d->d_fdesc4, f4.data(), f4.size() * sizeof(uint4), cudaMemcpyHostToDevice, d->stream));
+      CU(cudaMemcpyAsync(d->d_k2info, k2.data(), k2.size() * sizeof(int2), cudaMemcpyHostToDevice, d->stream));
+      CU(cudaStreamSynchronize(d->stream));
     }
   }
   // "safe" templates: at every refined level the clamp range is regular (max >= border) and every
@@ -640,7 +674,6 @@ static int prepare_bank(lm_detector* d) {
   if (nf) {
     CU(cudaMemcpyAsync(d->d_fbase, fbase.data(), nf * 4, cudaMemcpyHostToDevice, d->stream));
     CU(cudaMemcpyAsync(d->d_fxy, fxy.data(), nf * 4, cudaMemcpyHostToDevice, d->stream));
-    CU(cudaMemcpyAsync(d->d_fdesc, fdesc.data(), nf * sizeof(uint2), cudaMemcpyHostToDevice, d->stream));
   }
   if (d->G) CU(cudaMemcpyAsync(d->d_tslot, d->h_tslot.data(), sizeof(TSlot) * d->h_tslot.size(), cudaMemcpyHostToDevice, d->stream));
   CU(cudaStreamSynchronize(d->stream));  // host vectors go out of scope
@@ -796,7 +829,8 @@ static int size_levels(lm_detector* d, const int* rows, const int* cols, bool ne
         // label block: T*T*plane bits, then slack for the reads of lanes beyond the last word
         const size_t bits = (size_t)lv.T * lv.T * lv.plane;
         lv.lbw = (int)(((bits + 31) / 32 + 32 * (size_t)lv.rounds + 4 + 3) & ~(size_t)3);
-        const size_t words = (size_t)d->M * 8 * lv.lbw;
+        lv.bp_zero = (lv.nwords + 32 * lv.rounds + 8 + 3) & ~3;  // a lane reads words idx and idx + 1 of a window
+        const size_t words = (size_t)d->M * 8 * lv.lbw + lv.bp_zero;
         CU(cudaMalloc(&lv.d_bp, words * 4));
         CU(cudaMemsetAsync(lv.d_bp, 0, words * 4, d->stream));
       }
@@ -1095,9 +1129,10 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
     bool scan_fused = false;
     if (d->n_items_bits > 0) {
       BitScanParams bp;
-      bp.bp = low.d_bp; bp.bp_words = (uint32_t)((size_t)d->M * 8 * low.lbw);
+      bp.bp = low.d_bp; bp.bp_words = (uint32_t)((size_t)d->M * 8 * low.lbw + low.bp_zero);  // planes + the zero words
       bp.lbw = low.lbw; bp.plane = low.plane; bp.nwords = low.nwords;
-      bp.tslot = d->d_tslot; bp.fdesc = d->d_fdesc; bp.work = d->d_work;
+      bp.tslot = d->d_tslot; bp.fdesc4 = d->d_fdesc4; bp.k2info = d->d_k2info; bp.work = d->d_work;
+      bp.zero_off = (uint32_t)((size_t)d->M * 8 * low.lbw) * 4u;
       bp.items = d->d_items_bits; bp.n_items = d->n_items_bits;
       bp.S = d->S; bp.M = d->M; bp.slot_low = (d->L - 1) * d->M;
       bp.threshold = threshold;

@@ -429,7 +429,11 @@ struct BitScanParams {
   uint32_t bp_words;    // M*8*lbw
   int lbw, plane, nwords;
   const TSlot* tslot;
-  const uint2* fdesc;   // per feature: x = word of the H_o window start inside bp, y = shift | o << 8 | skip << 31
+  const uint4* fdesc4;  // per feature: byte offsets (inside bp) of the window start of its label's plane (x) and of the two
+                        // neighbouring labels' planes (y, z), bit shift (w); skipped features and the padding to a multiple
+                        // of 8 per (template, modality) point at the zero words behind the planes
+  const int2* k2info;   // [G][M]: first descriptor, padded count
+  uint32_t zero_off;    // byte offset of the zero words
   const int32_t* work;  // template id per work item
   const int32_t* items; // work items taken by this kernel
   int n_items;
@@ -702,30 +706,24 @@ __global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanPar
         uint32_t ch[8], cn[8];
 #pragma unroll
         for (int b = 0; b < 8; ++b) ch[b] = cn[b] = 0u;
+        const char* __restrict__ lane_base = reinterpret_cast<const char*>(bp + idx);  // this lane's word of every window
         for (int m = 0; m < p.M; ++m) {
-          const TSlot ts = p.tslot[(size_t)g * p.S + p.slot_low + m];
-          nfeat += ts.y;
-          const uint2* __restrict__ fd = p.fdesc + ts.x;
-          for (int f0 = 0; f0 < ts.y; f0 += 8) {
+          nfeat += p.tslot[(size_t)g * p.S + p.slot_low + m].y;
+          const int2 k2 = p.k2info[(size_t)g * p.M + m];
+          const uint4* __restrict__ fd = p.fdesc4 + k2.x;
+          for (int f0 = 0; f0 < k2.y; f0 += 8) {  // padded to a multiple of 8: no bounds check, no skip branch
             uint32_t xh[8], xn[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              uint2 d = make_uint2(0u, LM_SKIP_BIT);
-              if (f0 + u < ts.y) d = __ldg(fd + f0 + u);
-              if (d.y & LM_SKIP_BIT) {  // warp-uniform
-                xh[u] = xn[u] = 0u;
-              } else {
-                const int o = (d.y >> 8) & 7;
-                const uint32_t sft = d.y & 31u;
-                const uint32_t* __restrict__ ph = bp + d.x + idx;
-                const uint32_t* __restrict__ pm = ph + (((o + 7) & 7) - o) * p.lbw;
-                const uint32_t* __restrict__ pp = ph + (((o + 1) & 7) - o) * p.lbw;
-                const uint32_t h = __funnelshift_r(ph[0], ph[1], sft);
-                const uint32_t a = __funnelshift_r(pm[0], pm[1], sft);
-                const uint32_t b = __funnelshift_r(pp[0], pp[1], sft);
-                xh[u] = h;
-                xn[u] = (a | b) & ~h;
-              }
+              const uint4 d = __ldg(fd + f0 + u);  // warp-uniform
+              const uint32_t* __restrict__ ph = reinterpret_cast<const uint32_t*>(lane_base + d.x);
+              const uint32_t* __restrict__ pm = reinterpret_cast<const uint32_t*>(lane_base + d.y);
+              const uint32_t* __restrict__ pp = reinterpret_cast<const uint32_t*>(lane_base + d.z);
+              const uint32_t h = __funnelshift_r(ph[0], ph[1], d.w);
+              const uint32_t a = __funnelshift_r(pm[0], pm[1], d.w);
+              const uint32_t b = __funnelshift_r(pp[0], pp[1], d.w);
+              xh[u] = h;
+              xn[u] = (a | b) & ~h;
             }
             vc_add8(ch, xh);
             vc_add8(cn, xn);
@@ -751,28 +749,26 @@ __global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanPar
         uint32_t ch[8], cn[8];
 #pragma unroll
         for (int b = 0; b < 8; ++b) ch[b] = cn[b] = 0u;
+        const char* __restrict__ lane_base = reinterpret_cast<const char*>(bp + idx);
+        const uint4 zdesc = make_uint4(p.zero_off, p.zero_off, p.zero_off, 0u);
         for (int m = 0; m < p.M; ++m) {
-          const TSlot ts = p.tslot[(size_t)g * p.S + p.slot_low + m];
-          nfeat += ts.y;
-          const uint2* __restrict__ fd = p.fdesc + ts.x;
-          const int maxn = __reduce_max_sync(0xffffffffu, ts.y);
+          nfeat += p.tslot[(size_t)g * p.S + p.slot_low + m].y;
+          const int2 k2 = p.k2info[(size_t)g * p.M + m];
+          const uint4* __restrict__ fd = p.fdesc4 + k2.x;
+          const int maxn = __reduce_max_sync(0xffffffffu, k2.y);
           for (int f0 = 0; f0 < maxn; f0 += 8) {
             uint32_t xh[8], xn[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              uint2 d = make_uint2(0u, LM_SKIP_BIT);
-              if (f0 + u < ts.y) d = __ldg(fd + f0 + u);
-              const bool skip = (d.y & LM_SKIP_BIT) != 0u;
-              const int o = (d.y >> 8) & 7;
-              const uint32_t sft = d.y & 31u;
-              const uint32_t* __restrict__ ph = bp + (skip ? 0u : d.x) + idx;
-              const uint32_t* __restrict__ pm = ph + (((o + 7) & 7) - o) * (skip ? 0 : p.lbw);
-              const uint32_t* __restrict__ pp = ph + (((o + 1) & 7) - o) * (skip ? 0 : p.lbw);
-              const uint32_t h = __funnelshift_r(ph[0], ph[1], sft);
-              const uint32_t a = __funnelshift_r(pm[0], pm[1], sft);
-              const uint32_t b = __funnelshift_r(pp[0], pp[1], sft);
-              xh[u] = skip ? 0u : h;
-              xn[u] = skip ? 0u : ((a | b) & ~h);
+              const uint4 d = (f0 < k2.y) ? __ldg(fd + f0 + u) : zdesc;  // lanes of a shorter template read zeros
+              const uint32_t* __restrict__ ph = reinterpret_cast<const uint32_t*>(lane_base + d.x);
+              const uint32_t* __restrict__ pm = reinterpret_cast<const uint32_t*>(lane_base + d.y);
+              const uint32_t* __restrict__ pp = reinterpret_cast<const uint32_t*>(lane_base + d.z);
+              const uint32_t h = __funnelshift_r(ph[0], ph[1], d.w);
+              const uint32_t a = __funnelshift_r(pm[0], pm[1], d.w);
+              const uint32_t b = __funnelshift_r(pp[0], pp[1], d.w);
+              xh[u] = h;
+              xn[u] = (a | b) & ~h;
             }
             vc_add8(ch, xh);
             vc_add8(cn, xn);

@@ -417,7 +417,8 @@ def main():
     for n_ in nats:  # everything lazy (feature addresses for this frame size, work lists, buffers) now: no rank's
         n_.bind_quantized_device(ring[0][1], rows, cols)  # first frame lags the others' behind the barrier below
         n_.prepare()
-    cap = 16384
+    # records a shard may keep per frame (the fused exchange's blocks are fixed-size; N=1 grows its block on demand)
+    cap = 16384 if args.templates * args.objects * args.width * args.height <= 4000 * 640 * 480 else 1 << 17
     blk_bytes = 16 + 16 * cap
     fused = world > 1 and args.exchange == "fused"
     res = gathered = None
