@@ -22,7 +22,7 @@
 //
 // Pinning status: checked against the reference's own sources compiled
 // unmodified (oracle/_ref, see oracle/ref_shim/) on the reference's fixture
-// frame + banks; see tests/test_oracle_vs_ref.py and tests/golden/.
+// frame + banks; see tests/test_golden_and_ref.py and tests/golden/.
 //
 // Like the reference, accumulation uses 128-bit SSE2 adds (8 x u16 or 16 x u8
 // per instruction); x86-64 baseline, no -m flags needed.
