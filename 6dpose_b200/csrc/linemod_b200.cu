@@ -75,6 +75,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 #define LM_MAX_ROUNDS 5
 #define LM_BITS_SMEM_LIMIT (200 * 1024)
 #define LM_BAND_SMEM_LIMIT (160 * 1024)
+#define LM_K2_SMEM_MAX (222 * 1024)  // dynamic shared memory of k_coarse_packed: bit-planes + the teams' partial counters
 #define LM_CAND_DEFAULT (4ll << 20)  // candidate-list entries allocated up front (x 12 bytes)
 #define LM_TEV 7  // timing events per frame: start, K1, K2, scan, prep, filter, end
 
@@ -122,6 +123,7 @@ struct lm_detector {
   // refinement filter (k_refine_filter) on the first refined level lr = L - 2: column-major H-planes + descriptors
   bool filter_on = true;             // LINEMOD_B200_FILTER=0 switches it off (profiling / A-B runs)
   bool filter_ok = false;            // the current frame size / bank allow it
+  bool k2_split = true;              // LINEMOD_B200_K2_SPLIT=0: one warp per coarse-scan task whatever the shard
   bool planes_direct = true;         // LINEMOD_B200_PLANES_DIRECT=0: K1 always writes byte linear memories, k_refine_prep derives the planes
   int last_planes_level = -1;        // level the last K1 built in planes mode (its byte linear memories are stale)
   bool bits_exact = true;            // LINEMOD_B200_BITS_EXACT=0: survivors go to the byte-wise k_refine instead
@@ -257,7 +259,8 @@ extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** o
   // function attributes are per DEVICE: every handle raises the dynamic shared-memory limits on its own device
   // (a process may hold handles on several GPUs, e.g. lm_peer_connect_local across devices)
   CU(cudaFuncSetAttribute(k_linear_memories_band, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_BAND_SMEM_LIMIT));
-  CU(cudaFuncSetAttribute(k_coarse_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_BITS_SMEM_LIMIT + 4096));
+  CU(cudaFuncSetAttribute(k_coarse_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_K2_SMEM_MAX));
+  CU(cudaFuncSetAttribute(k_coarse_packed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
@@ -271,6 +274,8 @@ extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** o
   {
     const char* f = getenv("LINEMOD_B200_FILTER");
     d->filter_on = !(f && f[0] == '0');
+    const char* fks = getenv("LINEMOD_B200_K2_SPLIT");
+    d->k2_split = !(fks && fks[0] == '0');
     const char* fpd = getenv("LINEMOD_B200_PLANES_DIRECT");
     d->planes_direct = !(fpd && fpd[0] == '0');
     const char* fb = getenv("LINEMOD_B200_BITS_EXACT");
@@ -1147,22 +1152,34 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       bp.counters = d->d_counters;
       bp.queue = d->d_queue;
       bp.ticket = reinterpret_cast<int*>(d->d_counters + 3);
-      const size_t smem_bytes = (size_t)bp.bp_words * 4;
-      const bool smem = smem_bytes <= LM_BITS_SMEM_LIMIT;
-      // tasks of 32 words (full rounds + packed remainders).  One task per warp and one round per CTA: the CTA
-      // size follows the shard (24 warps for the whole bench bank on one GPU, 4-8 warps for a 1/8 shard), so a
-      // small shard spreads over all SMs instead of filling a few, and leaves registers to the other frames in
-      // flight.
+      const size_t plane_bytes = ((size_t)bp.bp_words * 4 + 15) & ~(size_t)15;
+      const bool smem = plane_bytes <= LM_BITS_SMEM_LIMIT;
+      // tasks of 32 words (full rounds + packed remainders).  One task per warp (or per TEAM of S warps when the shard has
+      // fewer tasks than the GPU has warp slots: the team deals the task's features, so the kernel's latency follows the
+      // shard) and one round per CTA: the CTA size follows the shard, so a small shard spreads over all SMs.
       const long long tasks = (long long)d->n_items_bits * (low.nwords / 32) +
                               ((long long)d->n_items_bits * (low.nwords % 32) + 31) / 32;
-      int wpc = (int)((tasks + d->sm_count - 1) / d->sm_count);
-      wpc = std::min(LM_PACK_THREADS / 32, std::max(4, (wpc + 3) & ~3));
-      const int grid = (int)std::max<long long>(1, std::min<long long>(d->sm_count, (tasks + wpc - 1) / wpc));
+      const long long slots = (long long)d->sm_count * (LM_PACK_THREADS / 32);
+      const size_t part_room = LM_K2_SMEM_MAX - (smem ? plane_bytes : (size_t)LM_K2_SMEM_MAX - 64 * 1024);
+      int S = 1;
+      while (d->k2_split && S < 8 && tasks * (S * 2) <= slots) {
+        const int S2 = S * 2;
+        long long w2 = (tasks * S2 + d->sm_count - 1) / d->sm_count;
+        w2 = std::min<long long>(LM_PACK_THREADS / 32, std::max<long long>(std::max(4, S2), (w2 + S2 - 1) / S2 * S2));
+        if ((size_t)(w2 / S2) * (S2 - 1) * 16 * 32 * 4 > part_room) break;
+        S = S2;
+      }
+      bp.split = S;
+      const int unit = std::max(4, S);
+      int wpc = (int)((tasks * S + d->sm_count - 1) / d->sm_count);
+      wpc = std::min(LM_PACK_THREADS / 32, std::max(unit, (wpc + unit - 1) / unit * unit));
+      const int grid = (int)std::max<long long>(1, std::min<long long>(d->sm_count, (tasks * S + wpc - 1) / wpc));
+      const size_t smem_bytes = (smem ? plane_bytes : 0) + (size_t)(wpc / S) * (S - 1) * 16 * 32 * 4;
       cudaError_t e = cudaSuccess;
       if (smem) {
         e = launch_pdl(k_coarse_packed<true>, dim3(grid), dim3(wpc * 32), smem_bytes, st, bp);
       } else {
-        e = launch_pdl(k_coarse_packed<false>, dim3(grid), dim3(wpc * 32), 0, st, bp);
+        e = launch_pdl(k_coarse_packed<false>, dim3(grid), dim3(wpc * 32), smem_bytes, st, bp);
       }
       if (e != cudaSuccess) return fail(LM_E_CUDA, "k_coarse_packed launch failed: %s", cudaGetErrorString(e));
       ++d->launches;

@@ -451,6 +451,7 @@ struct BitScanParams {
   unsigned long long* counters;
   int* queue;      // work / survivor counters of the refinement filter, reset with the header
   int* ticket;     // zero between launches
+  int split;       // warps per team (1, 2, 4 or 8): a task's features are dealt over the team (see k_coarse_packed)
 };
 
 #define CSA(sum, carry, a, b, c)                 \
@@ -602,6 +603,26 @@ __device__ __forceinline__ void coarse_emit(const BitScanParams& p, int w, int i
   if (my_count) atomicAdd(p.cnt + w, my_count);  // zero before the frame (k_scan_counts re-zeroes)
 }
 
+// bit-sliced add of two 8-bit vertical counters
+__device__ __forceinline__ void vc8_add(uint32_t (&c)[8], const uint32_t (&o)[8]) {
+  uint32_t carry = 0u;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const uint32_t a = c[b], x = o[b];
+    c[b] = a ^ x ^ carry;
+    carry = (a & x) | (carry & (a ^ x));
+  }
+}
+
+// barrier over the `nthreads` threads of one team of warps (named barrier `id`, 1..15)
+__device__ __forceinline__ void team_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Feature split (p.split = S > 1, small shards): S warps form a team that owns a task together; warp q of the team adds
+// the 8-feature steps q, q + S, ... of every modality, the partial counters meet in shared memory and warp 0 of the team
+// emits.  A task is then a chain S times shorter -- the latency of the kernel follows the shard instead of staying one
+// whole task (what keeps a 1/8 shard from being 8 times faster, and what holds an SM's shared memory for the duration).
 template <bool kSmem>
 __global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanParams p) {
   lm_pdl_wait();
@@ -611,6 +632,7 @@ __global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanPar
   __shared__ int s_rem[LM_PACK_CHUNK + 1];   // remainder words before template i
   __shared__ int s_warp[33];
   __shared__ int s_next;
+  __shared__ int s_team_task[LM_PACK_THREADS / 64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int t0 = (int)(((long long)p.n_items * blockIdx.x) / gridDim.x);
   const int t1 = (int)(((long long)p.n_items * (blockIdx.x + 1)) / gridDim.x);
@@ -668,7 +690,7 @@ __global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanPar
       if (threadIdx.x == 0) {
         s_full[nt] = tot_f;
         s_rem[nt] = tot_r;
-        s_next = nwarps;
+        s_next = nwarps / p.split;  // one task per team to start with
       }
     }
     __syncthreads();
@@ -687,7 +709,9 @@ __global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanPar
     }
     const int n_full = s_full[nt], rem_words = s_rem[nt];
     const int n_tasks = n_full + ((rem_words + 31) >> 5);
-    int task = warp;
+    const int S = p.split, q = warp & (S - 1), team = warp / S;
+    uint32_t* s_part = s_bp + (kSmem ? ((p.bp_words + 3u) & ~3u) : 0u) + (size_t)team * (S - 1) * 16 * 32;
+    int task = team;
     while (task < n_tasks) {
       if (task < n_full) {
         // ---- a full round: 32 consecutive words of ONE template, warp-uniform descriptors ----
@@ -711,7 +735,7 @@ __global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanPar
           nfeat += p.tslot[(size_t)g * p.S + p.slot_low + m].y;
           const int2 k2 = p.k2info[(size_t)g * p.M + m];
           const uint4* __restrict__ fd = p.fdesc4 + k2.x;
-          for (int f0 = 0; f0 < k2.y; f0 += 8) {  // padded to a multiple of 8: no bounds check, no skip branch
+          for (int f0 = q * 8; f0 < k2.y; f0 += 8 * S) {  // padded to a multiple of 8: no bounds check, no skip branch
             uint32_t xh[8], xn[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -729,7 +753,30 @@ __global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanPar
             vc_add8(cn, xn);
           }
         }
-        coarse_emit(p, w, idx, P, nfeat, words, ch, cn);
+        if (S > 1) {  // the team's partial counters meet
+          if (q > 0) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+              s_part[((q - 1) * 16 + b) * 32 + lane] = ch[b];
+              s_part[((q - 1) * 16 + 8 + b) * 32 + lane] = cn[b];
+            }
+          }
+          team_bar(team + 1, S * 32);
+          if (q == 0) {
+            for (int k = 0; k < S - 1; ++k) {
+              uint32_t oh[8], on[8];
+#pragma unroll
+              for (int b = 0; b < 8; ++b) {
+                oh[b] = s_part[(k * 16 + b) * 32 + lane];
+                on[b] = s_part[(k * 16 + 8 + b) * 32 + lane];
+              }
+              vc8_add(ch, oh);
+              vc8_add(cn, on);
+            }
+          }
+          team_bar(team + 1, S * 32);  // the partials are in registers: the others may overwrite them
+        }
+        if (q == 0) coarse_emit(p, w, idx, P, nfeat, words, ch, cn);
       } else {
         // ---- remainders: lane k owns entry e of the chunk's remainder words ----
         const int e = (task - n_full) * 32 + lane;
@@ -756,7 +803,7 @@ __global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanPar
           const int2 k2 = p.k2info[(size_t)g * p.M + m];
           const uint4* __restrict__ fd = p.fdesc4 + k2.x;
           const int maxn = __reduce_max_sync(0xffffffffu, k2.y);
-          for (int f0 = 0; f0 < maxn; f0 += 8) {
+          for (int f0 = q * 8; f0 < maxn; f0 += 8 * S) {
             uint32_t xh[8], xn[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -774,11 +821,40 @@ __global__ void __launch_bounds__(LM_PACK_THREADS, 1) k_coarse_packed(BitScanPar
             vc_add8(cn, xn);
           }
         }
-        if (active) coarse_emit(p, w, idx, P, nfeat, words, ch, cn);
+        if (S > 1) {  // the team's partial counters meet
+          if (q > 0) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+              s_part[((q - 1) * 16 + b) * 32 + lane] = ch[b];
+              s_part[((q - 1) * 16 + 8 + b) * 32 + lane] = cn[b];
+            }
+          }
+          team_bar(team + 1, S * 32);
+          if (q == 0) {
+            for (int k = 0; k < S - 1; ++k) {
+              uint32_t oh[8], on[8];
+#pragma unroll
+              for (int b = 0; b < 8; ++b) {
+                oh[b] = s_part[(k * 16 + b) * 32 + lane];
+                on[b] = s_part[(k * 16 + 8 + b) * 32 + lane];
+              }
+              vc8_add(ch, oh);
+              vc8_add(cn, on);
+            }
+          }
+          team_bar(team + 1, S * 32);  // the partials are in registers: the others may overwrite them
+        }
+        if (active && q == 0) coarse_emit(p, w, idx, P, nfeat, words, ch, cn);
       }
-      int nxt = 0;
-      if (lane == 0) nxt = atomicAdd(&s_next, 1);
-      task = __shfl_sync(0xffffffffu, nxt, 0);
+      if (S == 1) {
+        int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(&s_next, 1);
+        task = __shfl_sync(0xffffffffu, nxt, 0);
+      } else {
+        if (q == 0 && lane == 0) s_team_task[team] = atomicAdd(&s_next, 1);
+        team_bar(team + 1, S * 32);
+        task = s_team_task[team];
+      }
     }
     __syncthreads();  // the offset tables and s_next are rebuilt for the next chunk
   }
@@ -1732,7 +1808,7 @@ __device__ __forceinline__ void vc_add(uint32_t (&c)[LM_FILTER_BITS], const uint
 // Four warps share a survivor (a candidate is a chain of nf / 32 dependent steps, and the survivors are too few to hide
 // it with other warps): warp q of the quad takes the 32-feature steps q, q + 4, ..., the partial counters meet in shared
 // memory and warp 0 of the quad finishes the candidate.
-__global__ void __launch_bounds__(256, 3) k_refine_bits(RefineBitsParams p) {
+__global__ void __launch_bounds__(256, 4) k_refine_bits(RefineBitsParams p) {
   lm_pdl_wait();
   __shared__ uint32_t s_part[8][2 * LM_FILTER_BITS][32];
   const int lane = threadIdx.x & 31, gl = lane & 7, warp = threadIdx.x >> 5;

@@ -25,6 +25,11 @@ KEEP = [
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+    # on-chip traffic and pipes (round 2: what actually binds the bit-sliced kernels)
+    "l1tex__t_bytes.sum", "lts__t_bytes.sum", "lts__t_sectors.sum", "sm__inst_executed.avg.per_cycle_elapsed",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__warps_eligible.avg.per_cycle_active",
 ]
 STALL_PREFIX = "smsp__average_warps_issue_stalled_"
 STALL_SUFFIX = "_per_issue_active.ratio"
