@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblinemod_b200.so")
+# LINEMOD_B200_LIB: another build of the same library (A/B runs of compile-time variants); never a different backend
+LIB_PATH = os.environ.get("LINEMOD_B200_LIB") or os.path.join(_HERE, "csrc", "liblinemod_b200.so")
 
 LM_OK, LM_E_INVALID, LM_E_CUDA, LM_E_STATE, LM_E_CAPACITY = 0, -1, -2, -3, -4
 SHARD_CONTIGUOUS, SHARD_INTERLEAVED = 0, 1

@@ -1300,6 +1300,9 @@ __device__ __forceinline__ const uint32_t* lm_ptr_add(const char* base, uint32_t
 #ifndef LM_FILTER_MIN_CTAS
 #define LM_FILTER_MIN_CTAS 5
 #endif
+#ifndef LM_FILTER_CHUNK
+#define LM_FILTER_CHUNK 1  // consecutive candidates a warp takes from the queue at a time (2..16 measured: tail imbalance costs more than the L1 reuse buys)
+#endif
 // Layout contract with the host (prepare_bank / prepare_work): every template's descriptors are padded to a multiple of
 // 32 with descriptors that point into an all-zero tail of the plane buffer (so the loop needs no bounds predicate), and
 // finfo[w] = {first descriptor, features of the level, width | height << 16, flags | need << 8} with `need` computed on
@@ -1311,10 +1314,14 @@ __global__ void __launch_bounds__(256, LM_FILTER_MIN_CTAS) k_refine_filter_w(Fil
   const int T = p.ref.T, border = 8 * T;
   const int Wd = p.Wd;
   unsigned words_read = 0, dropped_feats = 0;
-  // the NEXT candidate's index, cell and per-template record are fetched while the current one is being counted
-  int c_next = 0;
-  if (lane == 0) c_next = atomicAdd(p.queue, 1);
-  c_next = __shfl_sync(0xffffffffu, c_next, 0);
+  // A warp takes LM_FILTER_CHUNK consecutive candidates at a time: the list is ordered by template, then cell, so they
+  // mostly share the template (descriptors) and their patches overlap (neighbouring cells) -- what the first one pulled
+  // into L1 serves the others.  The NEXT candidate's cell and per-template record are fetched while the current one is
+  // being counted.
+  int c_base = 0, k_in = 0;
+  if (lane == 0) c_base = atomicAdd(p.queue, LM_FILTER_CHUNK);
+  c_base = __shfl_sync(0xffffffffu, c_base, 0);
+  int c_next = c_base;
   uint2 e_next = make_uint2(0u, 0u);
   int4 fi_next = make_int4(0, 0, 0, 0);
   if (c_next < total) {
@@ -1326,8 +1333,12 @@ __global__ void __launch_bounds__(256, LM_FILTER_MIN_CTAS) k_refine_filter_w(Fil
     if (c >= total) break;
     const uint2 e = e_next;
     const int4 fi = fi_next;
-    if (lane == 0) c_next = atomicAdd(p.queue, 1);
-    c_next = __shfl_sync(0xffffffffu, c_next, 0);
+    if (++k_in == LM_FILTER_CHUNK) {
+      k_in = 0;
+      if (lane == 0) c_base = atomicAdd(p.queue, LM_FILTER_CHUNK);
+      c_base = __shfl_sync(0xffffffffu, c_base, 0);
+    }
+    c_next = c_base + k_in;
     if (c_next < total) {
       e_next = __ldcg(p.cand + c_next);
       fi_next = __ldg(p.finfo + e_next.x);
