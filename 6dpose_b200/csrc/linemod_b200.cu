@@ -123,6 +123,7 @@ struct lm_detector {
   // refinement filter (k_refine_filter) on the first refined level lr = L - 2: column-major H-planes + descriptors
   bool filter_on = true;             // LINEMOD_B200_FILTER=0 switches it off (profiling / A-B runs)
   bool filter_ok = false;            // the current frame size / bank allow it
+  long long k2_full_tasks = 0, k2_rem_words = 0;
   bool k2_split = true;              // LINEMOD_B200_K2_SPLIT=0: one warp per coarse-scan task whatever the shard
   bool planes_direct = true;         // LINEMOD_B200_PLANES_DIRECT=0: K1 always writes byte linear memories, k_refine_prep derives the planes
   int last_planes_level = -1;        // level the last K1 built in planes mode (its byte linear memories are stale)
@@ -707,6 +708,21 @@ static int prepare_work(lm_detector* d) {
     cudaFree(d->d_items_bytes); d->d_items_bytes = nullptr;
     d->n_items_bits = (int)ib.size();
     d->n_items_bytes = (int)iy.size();
+    // tasks of the bit-sliced coarse scan for this shard: a template has ceil(P / 32) useful position words, cut into
+    // full rounds of 32 words and a remainder (k_coarse_packed tabulates the same on the device)
+    d->k2_full_tasks = 0;
+    d->k2_rem_words = 0;
+    {
+      const int slot_low = (d->L - 1) * d->M;
+      const int nwords = d->lv[d->L - 1].nwords;
+      for (int32_t i : ib) {
+        const int g = d->shard_sel[(size_t)i];
+        const int P = d->h_tslot[(size_t)g * d->S + slot_low].z;
+        const int words = std::min(std::max((P + 31) >> 5, 1), nwords);
+        d->k2_full_tasks += words >> 5;
+        d->k2_rem_words += words & 31;
+      }
+    }
     if (!ib.empty()) {
       CU(cudaMalloc(&d->d_items_bits, sizeof(int32_t) * ib.size()));
       CU(cudaMemcpyAsync(d->d_items_bits, ib.data(), sizeof(int32_t) * ib.size(), cudaMemcpyHostToDevice, d->stream));
@@ -1157,8 +1173,7 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       // tasks of 32 words (full rounds + packed remainders).  One task per warp (or per TEAM of S warps when the shard has
       // fewer tasks than the GPU has warp slots: the team deals the task's features, so the kernel's latency follows the
       // shard) and one round per CTA: the CTA size follows the shard, so a small shard spreads over all SMs.
-      const long long tasks = (long long)d->n_items_bits * (low.nwords / 32) +
-                              ((long long)d->n_items_bits * (low.nwords % 32) + 31) / 32;
+      const long long tasks = std::max<long long>(1, d->k2_full_tasks + (d->k2_rem_words + 31) / 32);  // exact (prepare_work)
       const long long slots = (long long)d->sm_count * (LM_PACK_THREADS / 32);
       const size_t part_room = LM_K2_SMEM_MAX - (smem ? plane_bytes : (size_t)LM_K2_SMEM_MAX - 64 * 1024);
       int S = 1;
@@ -1170,10 +1185,12 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
         S = S2;
       }
       bp.split = S;
+      // every SM gets a CTA whenever there are enough tasks (templates are dealt to the CTAs evenly: a CTA short of
+      // warps for its tasks would need a second round), then as many warps as its share of the tasks
       const int unit = std::max(4, S);
-      int wpc = (int)((tasks * S + d->sm_count - 1) / d->sm_count);
+      const int grid = (int)std::max<long long>(1, std::min<long long>(d->sm_count, (tasks * S + unit - 1) / unit));
+      int wpc = (int)((tasks * S + grid - 1) / grid) + S;  // + one team: the static template split is not perfectly even
       wpc = std::min(LM_PACK_THREADS / 32, std::max(unit, (wpc + unit - 1) / unit * unit));
-      const int grid = (int)std::max<long long>(1, std::min<long long>(d->sm_count, (tasks * S + wpc - 1) / wpc));
       const size_t smem_bytes = (smem ? plane_bytes : 0) + (size_t)(wpc / S) * (S - 1) * 16 * 32 * 4;
       cudaError_t e = cudaSuccess;
       if (smem) {
