@@ -145,3 +145,49 @@ def test_reference_assertion_is_an_error(synth, oracle):
     nat = lib.NativeDetector(T)
     with pytest.raises(RuntimeError):
         nat.load_bank(packed, 4)
+
+
+@pytest.mark.parametrize("env", [
+    {"LINEMOD_B200_FILTER": "0"},                                   # no filter: byte-wise refinement of every candidate
+    {"LINEMOD_B200_BITS_EXACT": "0"},                               # filter, survivors refined byte-wise by four warps each
+    {"LINEMOD_B200_FILTER_VARIANT": "1"},                           # 8-lanes-per-candidate filter + byte-wise survivors
+    {"LINEMOD_B200_PLANES_DIRECT": "0"},                            # H-planes derived from the byte linear memories
+    {"LINEMOD_B200_K2_SPLIT": "0"},                                 # one warp per coarse task whatever the shard
+    {"LINEMOD_B200_PLANES_DIRECT": "0", "LINEMOD_B200_K2_SPLIT": "0", "LINEMOD_B200_BITS_EXACT": "0"},
+])
+def test_alternative_kernel_paths_bit_exact(synth, oracle, env, monkeypatch):
+    """Every switchable path (the fallbacks the default path replaced, kept for templates / pyramids it does not take and
+    for A/B runs) gives the oracle's result too.  The switches are read when the handle is created."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for T, W, H, nf, n, thr in (([4, 8], 640, 480, 150, 140, 75.0), ([5, 8], 640, 480, 63, 70, 70.0), ([2, 4, 8], 640, 512, 96, 35, 70.0)):
+        bank = synth.synth_bank(n, num_features=nf, levels=len(T), seed=21, class_ids=("01_template", "02_template"))
+        q, _ = synth.synth_frame(W, H, levels=len(T), seed=9, bank=bank, plant=6, T=T)
+        nat, packed = _native(T, bank)
+        got = nat.match_quantized(q, thr)
+        want, st = oracle.match(q, T, packed, thr, want_stats=True)
+        assert len(want) > 0
+        _assert_same(got, want)
+        c = nat.counters()
+        assert c["coarse_candidates"] == int(st["coarse_candidates"])
+        assert c["refine_bytes"] == int(st["refine_byte_adds"])
+        nat.close()
+
+
+def test_unsafe_templates_take_the_byte_path_next_to_the_bit_sliced_one(synth, oracle):
+    """A bank in which some templates are not eligible for the bit-sliced refinement (a feature outside the template box:
+    "unsafe") next to eligible ones: the filter hands the former to the byte-wise kernel (second survivor list), the
+    two exact kernels append to the same result block."""
+    T = [4, 8]
+    bank = synth.synth_bank(60, num_features=150, levels=2, seed=33)
+    tps = bank.classes["01_template"]
+    for k in range(0, 60, 3):
+        tps[k][0].features[5, 0] = tps[k][0].width + 6   # beyond the box: template k is "unsafe"
+    q, _ = synth.synth_frame(640, 480, levels=2, seed=12, bank=bank, plant=6, T=T)
+    nat, packed = _native(T, bank)
+    for thr in (70.0, 75.0):
+        got = nat.match_quantized(q, thr)
+        want, st = oracle.match(q, T, packed, thr, want_stats=True)
+        assert len(want) > 0
+        _assert_same(got, want)
+        assert nat.counters()["refine_bytes"] == int(st["refine_byte_adds"])
