@@ -25,7 +25,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-REF = sys.argv[1] if len(sys.argv) > 1 and os.path.isdir(sys.argv[1]) else "/root/reference"
+REF = os.environ.get("LM_REFERENCE_ROOT", "/root/reference")   # overridden by the command line when run as a script
 CASE = os.path.join(REF, "linemodLevelup", "test", "case1")
 
 K = np.array([[572.4114, 0.0, 325.2611], [0.0, 573.57043, 242.04899], [0.0, 0.0, 1.0]])  # test.cpp:106
@@ -113,4 +113,7 @@ def main(trace=None):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and os.path.isdir(os.path.join(sys.argv[1], "linemodLevelup")):
+        REF = sys.argv[1]
+        CASE = os.path.join(REF, "linemodLevelup", "test", "case1")
     main()
