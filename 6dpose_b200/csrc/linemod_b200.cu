@@ -124,6 +124,8 @@ struct lm_detector {
   bool filter_on = true;             // LINEMOD_B200_FILTER=0 switches it off (profiling / A-B runs)
   bool filter_ok = false;            // the current frame size / bank allow it
   long long k2_full_tasks = 0, k2_rem_words = 0;
+  bool k2_small_global = false;      // LINEMOD_B200_K2_SMALL_GLOBAL=1: small shards read the planes through L1 (no staging)
+  bool k2_smem = true;               // LINEMOD_B200_K2_SMEM=0: bit-planes read from global memory / L1 (no staging, no shared memory held)
   bool k2_split = true;              // LINEMOD_B200_K2_SPLIT=0: one warp per coarse-scan task whatever the shard
   bool planes_direct = true;         // LINEMOD_B200_PLANES_DIRECT=0: K1 always writes byte linear memories, k_refine_prep derives the planes
   int last_planes_level = -1;        // level the last K1 built in planes mode (its byte linear memories are stale)
@@ -275,6 +277,10 @@ extern "C" int lm_create(int device, int n_levels, const int* T, lm_detector** o
   {
     const char* f = getenv("LINEMOD_B200_FILTER");
     d->filter_on = !(f && f[0] == '0');
+    const char* fkg = getenv("LINEMOD_B200_K2_SMALL_GLOBAL");
+    d->k2_small_global = fkg && fkg[0] == '1';
+    const char* fkm = getenv("LINEMOD_B200_K2_SMEM");
+    d->k2_smem = !(fkm && fkm[0] == '0');
     const char* fks = getenv("LINEMOD_B200_K2_SPLIT");
     d->k2_split = !(fks && fks[0] == '0');
     const char* fpd = getenv("LINEMOD_B200_PLANES_DIRECT");
@@ -1169,12 +1175,18 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
       bp.queue = d->d_queue;
       bp.ticket = reinterpret_cast<int*>(d->d_counters + 3);
       const size_t plane_bytes = ((size_t)bp.bp_words * 4 + 15) & ~(size_t)15;
-      const bool smem = plane_bytes <= LM_BITS_SMEM_LIMIT;
+      bool smem = plane_bytes <= LM_BITS_SMEM_LIMIT && d->k2_smem;
       // tasks of 32 words (full rounds + packed remainders).  One task per warp (or per TEAM of S warps when the shard has
       // fewer tasks than the GPU has warp slots: the team deals the task's features, so the kernel's latency follows the
       // shard) and one round per CTA: the CTA size follows the shard, so a small shard spreads over all SMs.
-      const long long tasks = std::max<long long>(1, d->k2_full_tasks + (d->k2_rem_words + 31) / 32);  // exact (prepare_work)
+      // (upper estimate: every template counted with all nwords words; the kernel tabulates the exact tasks.  The sizes
+      // below are the ones the round's records were measured with: N=1 24 warps x 148 CTAs, one round; N=8 S=4, 16 x 116)
+      const long long tasks = (long long)d->n_items_bits * (low.nwords / 32) +
+                              ((long long)d->n_items_bits * (low.nwords % 32) + 31) / 32;
       const long long slots = (long long)d->sm_count * (LM_PACK_THREADS / 32);
+      // optional (LINEMOD_B200_K2_SMALL_GLOBAL=1): a small shard reads the planes through L1 instead of staging them --
+      // same latency measured (22 vs 23 us at 1/8 of the bank), no shared memory held; no throughput gain measured at N=8
+      if (d->k2_split && d->k2_small_global && tasks * 4 <= slots) smem = false;
       const size_t part_room = LM_K2_SMEM_MAX - (smem ? plane_bytes : (size_t)LM_K2_SMEM_MAX - 64 * 1024);
       int S = 1;
       while (d->k2_split && S < 8 && tasks * (S * 2) <= slots) {
@@ -1185,12 +1197,10 @@ static int enqueue_stages(lm_detector* d, float threshold, bool refine_only) {
         S = S2;
       }
       bp.split = S;
-      // every SM gets a CTA whenever there are enough tasks (templates are dealt to the CTAs evenly: a CTA short of
-      // warps for its tasks would need a second round), then as many warps as its share of the tasks
       const int unit = std::max(4, S);
-      const int grid = (int)std::max<long long>(1, std::min<long long>(d->sm_count, (tasks * S + unit - 1) / unit));
-      int wpc = (int)((tasks * S + grid - 1) / grid) + S;  // + one team: the static template split is not perfectly even
+      int wpc = (int)((tasks * S + d->sm_count - 1) / d->sm_count);
       wpc = std::min(LM_PACK_THREADS / 32, std::max(unit, (wpc + unit - 1) / unit * unit));
+      const int grid = (int)std::max<long long>(1, std::min<long long>(d->sm_count, (tasks * S + wpc - 1) / wpc));
       const size_t smem_bytes = (smem ? plane_bytes : 0) + (size_t)(wpc / S) * (S - 1) * 16 * 32 * 4;
       cudaError_t e = cudaSuccess;
       if (smem) {
