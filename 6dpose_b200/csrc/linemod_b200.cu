@@ -123,7 +123,6 @@ struct lm_detector {
   // refinement filter (k_refine_filter) on the first refined level lr = L - 2: column-major H-planes + descriptors
   bool filter_on = true;             // LINEMOD_B200_FILTER=0 switches it off (profiling / A-B runs)
   bool filter_ok = false;            // the current frame size / bank allow it
-  long long k2_full_tasks = 0, k2_rem_words = 0;
   bool k2_small_global = false;      // LINEMOD_B200_K2_SMALL_GLOBAL=1: small shards read the planes through L1 (no staging)
   bool k2_smem = true;               // LINEMOD_B200_K2_SMEM=0: bit-planes read from global memory / L1 (no staging, no shared memory held)
   bool k2_split = true;              // LINEMOD_B200_K2_SPLIT=0: one warp per coarse-scan task whatever the shard
@@ -714,21 +713,6 @@ static int prepare_work(lm_detector* d) {
     cudaFree(d->d_items_bytes); d->d_items_bytes = nullptr;
     d->n_items_bits = (int)ib.size();
     d->n_items_bytes = (int)iy.size();
-    // tasks of the bit-sliced coarse scan for this shard: a template has ceil(P / 32) useful position words, cut into
-    // full rounds of 32 words and a remainder (k_coarse_packed tabulates the same on the device)
-    d->k2_full_tasks = 0;
-    d->k2_rem_words = 0;
-    {
-      const int slot_low = (d->L - 1) * d->M;
-      const int nwords = d->lv[d->L - 1].nwords;
-      for (int32_t i : ib) {
-        const int g = d->shard_sel[(size_t)i];
-        const int P = d->h_tslot[(size_t)g * d->S + slot_low].z;
-        const int words = std::min(std::max((P + 31) >> 5, 1), nwords);
-        d->k2_full_tasks += words >> 5;
-        d->k2_rem_words += words & 31;
-      }
-    }
     if (!ib.empty()) {
       CU(cudaMalloc(&d->d_items_bits, sizeof(int32_t) * ib.size()));
       CU(cudaMemcpyAsync(d->d_items_bits, ib.data(), sizeof(int32_t) * ib.size(), cudaMemcpyHostToDevice, d->stream));
