@@ -2,12 +2,13 @@
 //
 // Reference being replaced: linemodLevelup::Detector::match and everything below it
 // (linemodLevelup/linemodLevelup.cpp of meiqua/6DPose @ 619be57, "LL.cpp"):
-//   kernels (lm_kernels.cuh): k_linear_memories, k_coarse_packed / k_coarse_bytes, k_scan_counts, k_refine
+//   kernels (lm_kernels.cuh): k_linear_memories_band, k_coarse_packed / k_coarse_bytes, k_scan_counts, k_refine_prep,
+//                             k_refine_filter_w, k_refine_bits / k_refine, k_peer_collect
 //   lm_finish (host)   <- std::sort + std::unique                       LL.cpp:1772-1774
 // Integer results (raw scores, x, y, template ids) are bit-exact; the float similarity is produced by
 // the same two IEEE operations as the reference ((raw * 100.f) / (4 * n)).
 //
-// No tensor cores: byte lookup / byte gather / 16-bit accumulate work.  No CPU fallback.
+// No tensor cores: bit-plane lookups / carry-save counters / small reductions.  No CPU fallback.
 
 #include "linemod_b200.h"
 

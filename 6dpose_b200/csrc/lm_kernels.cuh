@@ -1,12 +1,17 @@
 // lm_kernels.cuh -- device code of the LINEMOD match path (sm_100a).
 //
 // Reference functions replaced (linemodLevelup/linemodLevelup.cpp of meiqua/6DPose @ 619be57, "LL.cpp"):
-//   k_linear_memories  <- spread + computeResponseMaps + linearize          LL.cpp:1094-1243
+//   k_linear_memories(_band) <- spread + computeResponseMaps + linearize    LL.cpp:1094-1243
+//                         (bit-planes for the coarse scan, column-major H-planes for the refinement, byte linear
+//                          memories where something still reads them)
 //   k_coarse_packed    <- similarity(_64) + addSimilarities(_64) + threshold loop (bit-sliced)
 //   k_coarse_bytes     <- the same, byte-wise (templates the bit-sliced kernel does not take)
 //                                                                           LL.cpp:1284-1354, 1435-1534, 1836-1852
 //   k_scan_counts      <- candidates.push_back ordering (deterministic offsets)
-//   k_refine           <- similarityLocal(_64) + best-cell search + remove_if   LL.cpp:1366-1428, 1855-1938
+//   k_refine_prep      <- the candidate list in the reference's pre-sort order
+//   k_refine_filter(_w) + k_refine_bits <- similarityLocal(_64) + best-cell search + remove_if, bit-sliced: an exact
+//                         upper-bound filter, then exact scoring of its survivors      LL.cpp:1366-1428, 1855-1938
+//   k_refine<split>    <- the same, byte-wise (templates / pyramids the bit-sliced path does not take)
 #pragma once
 
 #include <cuda_runtime.h>

@@ -7,7 +7,7 @@ per-rank result blocks (kept records, 16 bytes each, with their global (work, se
 rank can then run the host finisher (lm_finish = the reference's std::sort + std::unique) on the
 concatenation.  Backends: NCCL on device tensors (GPUs), gloo on host tensors (CPU tests).
 
-On GPUs the exchange is FUSED into the refinement kernel (connect_peers): k_refine stores every kept
+On GPUs the exchange is FUSED into the exact refinement kernels (connect_peers): k_refine_bits / k_refine store every kept
 record straight into every rank's exchange buffer with peer stores over NVLink, a collector kernel on
 the same stream waits for all ranks' frame flags and packs the blocks -- the ordinary result block of
 each rank then already holds all shards' records; the process group only carries the one-time IPC

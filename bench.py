@@ -354,7 +354,7 @@ def workload_config(args, n):
             "templates": args.templates * args.objects, "objects": args.objects, "frame": [args.width, args.height],
             "threshold": args.threshold,
             "parallelism": "template-shard x%d (%s)" % (n, args.shards), "lanes": args.lanes,
-            "exchange": "none" if n == 1 else ("fused into k_refine (peer stores over NVLink + collector kernel)"
+            "exchange": "none" if n == 1 else ("fused into the exact refinement kernel (peer stores over NVLink + collector kernel)"
                                                if args.exchange == "fused" else "nccl all-gather of result blocks"),
             "l2": "ring of %d distinct frames (%.0f MB of label images > 126 MB L2); bank and linear memories are "
                   "L2-resident by design" % (args.ring, args.ring * (args.width * args.height * 2 * 1.25) / 1e6)}
@@ -423,7 +423,7 @@ def main():
     fused = world > 1 and args.exchange == "fused"
     res = gathered = None
     if fused:
-        # exchange fused into k_refine: peer stores into every rank's exchange buffer (CUDA IPC mappings over
+        # exchange fused into the refinement kernels: peer stores into every rank's exchange buffer (CUDA IPC mappings over
         # NVLink) + a collector kernel; the process group only carries the IPC handles, once
         for n_ in nats:
             handles = [None] * world

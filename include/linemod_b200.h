@@ -132,15 +132,18 @@ int lm_prepare(lm_detector* d);
 int lm_set_result_buffer(lm_detector* d, void* d_block, int64_t capacity_records);
 int lm_device_result(lm_detector* d, void** d_block, int64_t* capacity_records);
 
-/* Multi-GPU exchange fused into the refinement kernel (one process per GPU, template shards from
+/* Multi-GPU exchange fused into the refinement kernels (one process per GPU, template shards from
  * lm_select; the reference has no counterpart: its template loop is serial, LL.cpp:1797).  Every rank
- * owns an exchange buffer of 2 frame slots x `world` result blocks; once connected, k_refine stores every
- * kept record into the block [slot][rank] of EVERY rank's buffer with peer stores over NVLink (local
+ * owns an exchange buffer of 2 frame slots x `world` result blocks; once connected, the exact refinement
+ * kernel (k_refine_bits / k_refine) stores every kept record into the block [slot][rank] of EVERY rank's buffer with peer stores over NVLink (local
  * stores for itself), its last CTA publishes the block header and a frame sequence flag, and a collector
  * kernel on the same stream waits for all `world` flags and packs the blocks into this handle's result
  * block.  lm_complete / lm_fetch_records / lm_device_result then see the kept records of ALL shards: no
  * separate collective, no host round trip between refinement and exchange.  All ranks must enqueue the
- * same frames in the same order (SPMD); capacity_records is per rank and per frame.
+ * same frames in the same order (SPMD); capacity_records is per rank and per frame.  A collector that waits
+ * longer than LINEMOD_B200_PEER_TIMEOUT_MS (default 1000) for a peer fails the frame (LM_E_STATE from
+ * lm_complete) and raises a per-device abort flag every later collector honours at once; lm_peer_export
+ * clears it.
  *   lm_peer_export        allocate the buffer, return its CUDA IPC handle (LM_PEER_HANDLE_BYTES bytes)
  *   lm_peer_connect       handles[world][LM_PEER_HANDLE_BYTES] of all ranks (own entry ignored)
  *   lm_peer_connect_local same, for handles living in ONE process: bases[world] from lm_peer_base
