@@ -264,6 +264,16 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_point_to_plane(const IcpJob
       double best = max_d2;  // radius search, strict <
       int bj = -1;
       for (int t0 = 0; t0 < nt; t0 += ICP_TILE) {
+        // The target cloud is sorted by voxel, x major (voxel_down_sample), so a tile covers the x range
+        // [x(first) - voxel, x(last) + voxel]: a tile whose range is farther from EVERY source point of this pass than its
+        // best squared distance so far cannot change any correspondence (strict <) and is skipped -- exact, and most
+        // tiles go: the search radius is 1 cm, the cloud is ~10 cm wide
+        {
+          const int last = min(t0 + ICP_TILE, nt) - 1;
+          const double tmin = Q[(size_t)3 * t0] - ICP_VOXEL, tmax = Q[(size_t)3 * last] + ICP_VOXEL;
+          const double gap = !live ? 1e300 : (px < tmin ? tmin - px : (px > tmax ? px - tmax : 0.0));
+          if (__syncthreads_and(!live || gap * gap >= best)) continue;
+        }
         __syncthreads();
         for (int k = threadIdx.x; k < ICP_TILE * 3; k += blockDim.x) (&s_t[0][0])[k] = (t0 + k / 3) < nt ? Q[(size_t)3 * t0 + k] : 0.0;
         __syncthreads();
