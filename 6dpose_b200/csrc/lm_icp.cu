@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <limits>
+#include <thread>
 #include <vector>
 
 int lm_fail(int code, const char* fmt, ...);  // linemod_b200.cu
@@ -540,10 +541,22 @@ extern "C" int lm_icp_process_batch(lm_icp* h, int n_hyp, const uint16_t* scene_
   std::vector<int> job_of((size_t)n_hyp, -1);
   std::vector<double> all;
   int max_count = 0;
-  for (int i = 0; i < n_hyp; ++i) {
+  for (int i = 0; i < n_hyp; ++i)
     if (!model_depths[i]) return lm_fail(LM_E_INVALID, "model_depths[%d] is null", i);
-    build_cloud(scene_depth, srows, scols, model_depths[i], mrows, mcols, sceneK, modelK + 9 * i, R + 9 * i, t + 3 * i,
-                detect_xy[2 * i], detect_xy[2 * i + 1], h->use_scene_cloud, clouds[i]);
+  {
+    // the hypotheses' clouds are independent: hypothesis 0 on this thread, the others on their own (a batch is the three
+    // NMS survivors of the drivers, linemod_and_levelup_test.py:348-367)
+    auto build = [&](int i) {
+      build_cloud(scene_depth, srows, scols, model_depths[i], mrows, mcols, sceneK, modelK + 9 * i, R + 9 * i, t + 3 * i,
+                  detect_xy[2 * i], detect_xy[2 * i + 1], h->use_scene_cloud, clouds[i]);
+    };
+    std::vector<std::thread> workers;
+    for (int i = 1; i < n_hyp && i < 16; ++i) workers.emplace_back(build, i);
+    if (n_hyp > 0) build(0);
+    for (int i = 16; i < n_hyp; ++i) build(i);
+    for (std::thread& w : workers) w.join();
+  }
+  for (int i = 0; i < n_hyp; ++i) {
     if (clouds[i].early) continue;
     IcpJob j;
     j.src_first = (int32_t)(all.size() / 3);
