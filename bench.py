@@ -171,7 +171,7 @@ def run_reference(args):
     name, kind = best_cpu_arm(arms)
     fps = arms[name]["fps"]
     out = {
-        "impl": "reference", "metric": "frames/sec @640x480, 3115-template bank, Detector::match after quantization",
+        "impl": "reference", "metric": metric_name(args),
         "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": n_frames, "warmup": 1,
         "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8/u16", "data": "synthetic",
@@ -345,6 +345,11 @@ def pose_pipeline(lib, local):
         out["pose_rel_error_vs_icp_oracle_max"] = repr(e)
     nat.close()
     return out
+
+
+def metric_name(args):
+    return "frames/sec @%dx%d, %d-template bank, Detector::match after quantization" % (
+        args.width, args.height, args.templates * max(args.objects, 1))
 
 
 def workload_config(args, n):
@@ -741,7 +746,7 @@ def main():
         },
     }
     out = {
-        "metric": "frames/sec @640x480, 3115-template bank, Detector::match after quantization",
+        "metric": metric_name(args),
         "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8/u16", "data": "synthetic", "config": workload_config(args, world),
